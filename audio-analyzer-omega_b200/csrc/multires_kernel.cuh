@@ -1,0 +1,161 @@
+// multires_kernel.cuh -- batched windowed real FFT with fused |X| * weight epilogue and fused
+// combine (np.interp onto the linear target grid) for ONE resolution.
+//
+// Replaces, for a whole batch of (channel, hop) frames at once:
+//   MultiResolutionFFT.process_audio_chunk   (omega4/audio/multi_resolution_fft.py:251-286)
+//   MultiResolutionFFT._apply_psychoacoustic_weighting (:304-333, weights precomputed on host)
+//   MultiResolutionFFT.combine_results_optimized       (:359-395, tables precomputed on host)
+//   BatchedFFTProcessor._process_size_group_cpu/gpu     (omega4/optimization/batched_fft_processor.py:197-285)
+//   GPUAcceleratedFFT.compute_fft / process_fft_batch   (omega4/optimization/gpu_accelerated_fft.py:92-177,300-340)
+#pragma once
+#include "fft_core.cuh"
+
+namespace o4 {
+
+struct MultiresArgs {
+    const float* x;            // samples; frame f of channel c starts at x + c*ch_stride + f*frame_stride + frame_off0
+    long long ch_stride;
+    long long frame_stride;
+    long long frame_off0;      // hop mode: hop - N (negative: reaches into history before x)
+    int n_ch;
+    int n_frames;              // frames per channel
+    int first_frame;           // frames < first_frame are "not filled yet": zero outputs
+    int rounds;                // rounds per CTA (each round = CONC frames)
+    const float* window;       // [N] or nullptr
+    const float* binw;         // [M+1] per-bin weights or nullptr
+    const float2* twM;         // [M]      exp(-2 pi i e / M)
+    const float2* twN;         // [M/2+1]  exp(-2 pi i k / N)
+    float* mag_out;            // [n_ch][n_frames][M+1] or nullptr
+    float2* cplx_out;          // [n_ch][n_frames][M+1] or nullptr
+    float* comb_out;           // [n_ch][n_frames][T] or nullptr
+    int T;
+    int n_tb;                  // target bins written by this resolution
+    const int* tb_idx;         // [n_tb] target bin index
+    const int* tb_lo;          // [n_tb] lower FFT bin (or -1: write 0)
+    const float* tb_frac;      // [n_tb] interpolation fraction
+    float wnum, wden;          // out = interp * wnum / wden
+    int need_lo, need_cnt;     // FFT bins [need_lo, need_lo + need_cnt) feed the combine step
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(FftShape<LOG2M>::NT, (FftShape<LOG2M>::NT <= 256 ? 2 : 1))
+multires_kernel(const __grid_constant__ MultiresArgs a) {
+    using S = FftShape<LOG2M>;
+    constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufs = reinterpret_cast<float2*>(smem_raw);
+    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * 2 * BUF);
+
+    const int tid = threadIdx.x;
+    const int g = tid / TPF;
+    const int t = tid % TPF;
+    float2* buf0 = bufs + (size_t)g * 2 * BUF;
+    float2* buf1 = buf0 + BUF;
+    float* mags = mags_all + (size_t)g * a.need_cnt;
+
+    const int frames_per_cta = a.rounds * CONC;
+    const int tiles_per_ch = (a.n_frames + frames_per_cta - 1) / frames_per_cta;
+    const int ch = blockIdx.x / tiles_per_ch;
+    const int tile = blockIdx.x % tiles_per_ch;
+    const int f0 = tile * frames_per_cta;
+
+    // per-thread constants: window pairs for the 16 owned inputs, stage twiddles
+    float2 win[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
+    StageTw<LOG2M> st;
+    load_stage_twiddles<LOG2M>(st, a.twM, t);
+
+    const float* xch = a.x + (long long)ch * a.ch_stride + a.frame_off0;
+    const bool all_bins = (a.mag_out != nullptr) || (a.cplx_out != nullptr);
+    const int need_hi = a.need_lo + a.need_cnt;   // exclusive
+
+    float2 v[16];
+    {
+        int f = f0 + g;
+        if (f < a.n_frames && f >= a.first_frame) {
+            const float2* px = reinterpret_cast<const float2*>(xch + (long long)f * a.frame_stride);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
+        }
+    }
+
+    for (int r = 0; r < a.rounds; ++r) {
+        const int f = f0 + r * CONC + g;
+        const bool valid = f < a.n_frames;
+        const bool active = valid && f >= a.first_frame;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j].x *= win[j].x; v[j].y *= win[j].y; }
+        }
+        const float2* Z = fft_forward<LOG2M, false>(v, buf0, buf1, st, t, active);
+
+        // prefetch the next round's samples; they land while the epilogue runs
+        {
+            int fn = f + CONC;
+            if (r + 1 < a.rounds && fn < a.n_frames && fn >= a.first_frame) {
+                const float2* px = reinterpret_cast<const float2*>(xch + (long long)fn * a.frame_stride);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
+            }
+        }
+
+        const size_t row = (size_t)ch * a.n_frames + (valid ? f : 0);
+        if (valid) {
+            float* mrow = a.mag_out ? a.mag_out + row * (M + 1) : nullptr;
+            float2* crow = a.cplx_out ? a.cplx_out + row * (M + 1) : nullptr;
+            // pairs u = t + i*TPF in [0, M/2), plus u = M/2 handled by thread 0 as a 9th pair
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                int u = (i < 8) ? t + i * TPF : M / 2;
+                if (i == 8 && t != 0) break;
+                int k = u, km = M - u;
+                bool nk = all_bins || (k >= a.need_lo && k < need_hi);
+                bool nm = all_bins || (km >= a.need_lo && km < need_hi);
+                if (!(nk || nm)) continue;
+                float mk = 0.f, mm = 0.f;
+                float2 Xk = make_float2(0.f, 0.f), Xm = Xk;
+                if (active) {
+                    float2 Zk = Z[padi(u)];
+                    float2 Zm = Z[padi((M - u) & (M - 1))];
+                    float2 w = __ldg(a.twN + u);
+                    rfft_pair(Zk, Zm, w, Xk, Xm);
+                    mk = cabs(Xk);
+                    mm = cabs(Xm);
+                    if (a.binw) { mk *= __ldg(a.binw + k); mm *= __ldg(a.binw + km); }
+                }
+                if (mrow) { mrow[k] = mk; mrow[km] = mm; }
+                if (crow) { crow[k] = Xk; crow[km] = Xm; }
+                if (k >= a.need_lo && k < need_hi) mags[k - a.need_lo] = mk;
+                if (km >= a.need_lo && km < need_hi) mags[km - a.need_lo] = mm;
+            }
+        }
+        __syncthreads();
+        if (valid && a.comb_out) {
+            float* orow = a.comb_out + row * a.T;
+            for (int j = t; j < a.n_tb; j += TPF) {
+                int lo = __ldg(a.tb_lo + j);
+                float val = 0.f;
+                if (active && lo >= 0) {
+                    float m0 = mags[lo - a.need_lo];
+                    float m1 = mags[lo + 1 - a.need_lo];
+                    float vi = fmaf(m1 - m0, __ldg(a.tb_frac + j), m0);
+                    val = (vi * a.wnum) / a.wden;
+                }
+                orow[__ldg(a.tb_idx + j)] = val;
+            }
+        }
+        // No second barrier needed: every thread has finished reading Z before the barrier above,
+        // and the next epilogue's writes to mags are separated from this combine's reads by the
+        // barriers inside fft_forward.
+    }
+}
+
+template <int LOG2M>
+inline size_t multires_smem_bytes(int need_cnt) {
+    using S = FftShape<LOG2M>;
+    return (size_t)S::CONC * 2 * S::BUF * sizeof(float2) + (size_t)S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float);
+}
+
+}  // namespace o4

@@ -1,0 +1,806 @@
+// omega4_cuda.cu -- host side of libomega4_cuda.so: the C ABI declared in include/omega4_cuda.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/omega4_cuda.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fft_core.cuh"
+#include "kweight_kernel.cuh"
+#include "misc_kernels.cuh"
+#include "multires_kernel.cuh"
+#include "stats_kernel.cuh"
+#include "truepeak_kernel.cuh"
+
+using namespace o4;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                     __FILE__, __LINE__);                                                          \
+            return fail(OMEGA4_ERR_CUDA, b__);                                                     \
+        }                                                                                          \
+    } while (0)
+
+extern "C" const char* omega4_last_error(void) { return g_err.c_str(); }
+extern "C" int omega4_abi_version(void) { return OMEGA4_ABI_VERSION; }
+extern "C" int omega4_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// ------------------------------------------------------------------------------------------
+// twiddle tables, cached per (device, log2M)
+// ------------------------------------------------------------------------------------------
+struct Twiddles { float2* twM = nullptr; float2* twN = nullptr; float2* tw4W = nullptr; };
+static std::mutex g_tw_mu;
+static std::map<std::pair<int, int>, Twiddles> g_tw;
+
+static int get_twiddles(int device, int log2m, Twiddles* out) {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto key = std::make_pair(device, log2m);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) { *out = it->second; return OMEGA4_OK; }
+    const int M = 1 << log2m, N = 2 * M;
+    const double two_pi = 6.283185307179586476925287;
+    std::vector<float2> a(M), b(M / 2 + 1), c(3 * M + 1);
+    for (int e = 0; e < M; ++e) a[e] = make_float2((float)cos(two_pi * e / M), (float)-sin(two_pi * e / M));
+    for (int k = 0; k <= M / 2; ++k) b[k] = make_float2((float)cos(two_pi * k / N), (float)-sin(two_pi * k / N));
+    for (int j = 0; j <= 3 * M; ++j) c[j] = make_float2((float)cos(two_pi * j / (4.0 * N)), (float)sin(two_pi * j / (4.0 * N)));
+    Twiddles t;
+    CK(cudaMalloc(&t.twM, a.size() * sizeof(float2)));
+    CK(cudaMalloc(&t.twN, b.size() * sizeof(float2)));
+    CK(cudaMalloc(&t.tw4W, c.size() * sizeof(float2)));
+    CK(cudaMemcpy(t.twM, a.data(), a.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.twN, b.data(), b.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.tw4W, c.data(), c.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    g_tw[key] = t;
+    *out = t;
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launch dispatch over the transform size
+// ------------------------------------------------------------------------------------------
+template <int L>
+static int launch_multires_t(const MultiresArgs& a, cudaStream_t s) {
+    using S = FftShape<L>;
+    const size_t smem = multires_smem_bytes<L>(a.need_cnt);
+    CK(cudaFuncSetAttribute(multires_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fpc = a.rounds * S::CONC;
+    const long long tiles = (a.n_frames + fpc - 1) / fpc;
+    const long long grid = tiles * a.n_ch;
+    if (grid <= 0) return OMEGA4_OK;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "multires grid too large");
+    multires_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+static int launch_multires(int log2m, const MultiresArgs& a, cudaStream_t s) {
+    switch (log2m) {
+        case 8: return launch_multires_t<8>(a, s);
+        case 9: return launch_multires_t<9>(a, s);
+        case 10: return launch_multires_t<10>(a, s);
+        case 11: return launch_multires_t<11>(a, s);
+        case 12: return launch_multires_t<12>(a, s);
+        case 13: return launch_multires_t<13>(a, s);
+        case 14: return launch_multires_t<14>(a, s);
+    }
+    return fail(OMEGA4_ERR_UNSUPPORTED, "fft size must be a power of two in 512 .. 32768");
+}
+
+static int default_rounds(int n_frames, int conc) {
+    // enough rounds to amortise the per-thread window/twiddle loads, few enough to keep the grid large
+    int r = 16;
+    while (r > 1 && (long long)r * conc > n_frames) r >>= 1;
+    return r;
+}
+
+static int launch_truepeak(const TruePeakArgs& a, cudaStream_t s) {
+    constexpr int L = 10;     // W = 2048 -> 1024 complex points
+    using S = FftShape<L>;
+    const size_t smem = truepeak_smem_bytes<L>();
+    CK(cudaFuncSetAttribute(truepeak_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fpc = a.rounds * S::CONC;
+    const long long grid = (long long)((a.n_frames + fpc - 1) / fpc) * a.n_ch;
+    if (grid <= 0) return OMEGA4_OK;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "truepeak grid too large");
+    truepeak_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+static int launch_kweight(const KweightArgs& a, cudaStream_t s) {
+    const size_t smem = kweight_smem_bytes();
+    CK(cudaFuncSetAttribute(kweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fpc = a.frames_per_warp * KW_WARPS;
+    const long long grid = (long long)((a.n_frames + fpc - 1) / fpc) * a.n_ch;
+    if (grid <= 0) return OMEGA4_OK;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "kweight grid too large");
+    kweight_kernel<<<(unsigned)grid, KW_WARPS * 32, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+static int launch_stats(const StatsArgs& a, cudaStream_t s) {
+    const size_t smem = stats_smem_bytes();
+    CK(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.n_ch <= 0) return OMEGA4_OK;
+    stats_kernel<<<a.n_ch, ST_THREADS, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K-weighting scan tables
+// ------------------------------------------------------------------------------------------
+static void mat2_mul(const double* a, const double* b, double* c) {
+    double r[4] = {a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3],
+                   a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]};
+    memcpy(c, r, sizeof r);
+}
+
+static void build_biquad(const double* b, const double* a, KwBiquad* q) {
+    const double a0 = a[0];
+    q->b0 = b[0] / a0; q->b1 = b[1] / a0; q->b2 = b[2] / a0;
+    q->a1 = a[1] / a0; q->a2 = a[2] / a0;
+    // lfilter_zi: (I - companion(a)^T) zi = b[1:] - a[1:] b[0]
+    {
+        const double m00 = 1.0 + q->a1, m01 = -1.0, m10 = q->a2, m11 = 1.0;
+        const double r0 = q->b1 - q->a1 * q->b0, r1 = q->b2 - q->a2 * q->b0;
+        const double det = m00 * m11 - m01 * m10;
+        q->zi0 = (r0 * m11 - m01 * r1) / det;
+        q->zi1 = (m00 * r1 - m10 * r0) / det;
+    }
+    // state transition of transposed direct form II: z' = A z + B x, y = z1 + b0 x
+    const double A[4] = {-q->a1, 1.0, -q->a2, 0.0};
+    double P[4] = {1.0, 0.0, 0.0, 1.0};
+    double A14[4] = {1, 0, 0, 1};
+    for (int i = 0; i < KW_L; ++i) {
+        q->g[i][0] = P[0];
+        q->g[i][1] = P[1];
+        if (i == KW_SLACK) memcpy(A14, P, sizeof P);
+        mat2_mul(A, P, P);
+    }
+    memcpy(q->phi[0], P, sizeof P);              // A^65
+    for (int j = 1; j < 5; ++j) mat2_mul(q->phi[j - 1], q->phi[j - 1], q->phi[j]);
+    const double det = A14[0] * A14[3] - A14[1] * A14[2];
+    q->ainv[0] = A14[3] / det; q->ainv[1] = -A14[1] / det;
+    q->ainv[2] = -A14[2] / det; q->ainv[3] = A14[0] / det;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct ResInfo {
+    int n = 0, log2m = 0, bins = 0;
+    float weight = 1.f;
+    float* window = nullptr;
+    float* binw = nullptr;
+    int n_tb = 0;                 // entries in the device tables (incl. orphans on resolution 0)
+    int* tb_idx = nullptr;
+    int* tb_lo = nullptr;
+    float* tb_frac = nullptr;
+    int need_lo = 0, need_cnt = 0;
+    Twiddles tw;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return OMEGA4_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return OMEGA4_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct KernelTime { char name[32]; cudaEvent_t e0, e1; };
+
+struct omega4_plan {
+    int device = 0;
+    int sample_rate = 48000, hop = 512, n_res = 0, T = 0, W = OMEGA4_METER_WINDOW;
+    double gate = -70.0;
+    ResInfo res[OMEGA4_MAX_RES];
+    bool disjoint = true;
+    // general combine CSR
+    int* csr_ptr = nullptr; int* csr_res = nullptr; int* csr_lo = nullptr; float* csr_frac = nullptr;
+    double* hann64 = nullptr;
+    float* hann32 = nullptr;
+    KwBiquad kw[2];
+    Twiddles tw_meter;
+    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES];
+    DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
+    long long launches = 0;
+    std::vector<KernelTime> times;
+    size_t n_times = 0;
+};
+
+static int upload(void** dst, const void* src, size_t bytes) {
+    CK(cudaMalloc(dst, bytes ? bytes : 1));
+    if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return OMEGA4_OK;
+}
+
+static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
+    if (d->n_res < 1 || d->n_res > OMEGA4_MAX_RES) return fail(OMEGA4_ERR_INVALID, "n_res must be 1..8");
+    if (d->hop <= 0 || (d->hop % 4) != 0) return fail(OMEGA4_ERR_INVALID, "hop must be a positive multiple of 4");
+    if (d->target_bins < 1) return fail(OMEGA4_ERR_INVALID, "target_bins must be >= 1");
+    if (d->meter_window != OMEGA4_METER_WINDOW) return fail(OMEGA4_ERR_UNSUPPORTED, "meter_window must be 2048");
+    if (!d->fft_sizes || !d->windows || !d->tb_count || !d->res_weight || !d->meter_hann || !d->kw_coeffs)
+        return fail(OMEGA4_ERR_INVALID, "plan_desc has NULL tables");
+    p->sample_rate = d->sample_rate; p->hop = d->hop; p->n_res = d->n_res; p->T = d->target_bins;
+    p->gate = d->gate_threshold;
+    std::vector<int> owners(d->target_bins, 0);
+    size_t woff = 0, boff = 0, toff = 0;
+    std::vector<std::vector<int>> idx(d->n_res), lo(d->n_res);
+    std::vector<std::vector<float>> fr(d->n_res);
+    for (int r = 0; r < d->n_res; ++r) {
+        ResInfo& ri = p->res[r];
+        const int n = d->fft_sizes[r];
+        if (!is_pow2(n) || n < 512 || n > 32768) return fail(OMEGA4_ERR_UNSUPPORTED, "fft size must be a power of two in 512 .. 32768");
+        ri.n = n; ri.log2m = ilog2(n) - 1; ri.bins = n / 2 + 1; ri.weight = d->res_weight[r];
+        if (ri.weight <= 0.f) return fail(OMEGA4_ERR_INVALID, "resolution weight must be positive");
+        int rc = upload((void**)&ri.window, d->windows + woff, (size_t)n * sizeof(float));
+        if (rc) return rc;
+        if (d->bin_weights) { rc = upload((void**)&ri.binw, d->bin_weights + boff, (size_t)ri.bins * sizeof(float)); if (rc) return rc; }
+        woff += n; boff += ri.bins;
+        const int cnt = d->tb_count[r];
+        if (cnt < 0) return fail(OMEGA4_ERR_INVALID, "negative tb_count");
+        for (int j = 0; j < cnt; ++j) {
+            const int ti = d->tb_idx[toff + j], l = d->tb_lo[toff + j];
+            if (ti < 0 || ti >= d->target_bins || l < 0 || l + 1 >= ri.bins)
+                return fail(OMEGA4_ERR_INVALID, "combine table entry out of range");
+            idx[r].push_back(ti); lo[r].push_back(l); fr[r].push_back(d->tb_frac[toff + j]);
+            owners[ti]++;
+        }
+        toff += cnt;
+        rc = get_twiddles(p->device, ri.log2m, &ri.tw);
+        if (rc) return rc;
+    }
+    p->disjoint = true;
+    for (int t = 0; t < d->target_bins; ++t) if (owners[t] > 1) p->disjoint = false;
+    // CSR for the general combine kernel (entries in resolution order, as `results` is iterated)
+    {
+        std::vector<int> ptr(d->target_bins + 1, 0), cres, clo;
+        std::vector<float> cfr;
+        for (int t = 0; t < d->target_bins; ++t) {
+            for (int r = 0; r < d->n_res; ++r)
+                for (size_t j = 0; j < idx[r].size(); ++j)
+                    if (idx[r][j] == t) { cres.push_back(r); clo.push_back(lo[r][j]); cfr.push_back(fr[r][j]); }
+            ptr[t + 1] = (int)cres.size();
+        }
+        int rc = upload((void**)&p->csr_ptr, ptr.data(), ptr.size() * sizeof(int)); if (rc) return rc;
+        rc = upload((void**)&p->csr_res, cres.data(), cres.size() * sizeof(int)); if (rc) return rc;
+        rc = upload((void**)&p->csr_lo, clo.data(), clo.size() * sizeof(int)); if (rc) return rc;
+        rc = upload((void**)&p->csr_frac, cfr.data(), cfr.size() * sizeof(float)); if (rc) return rc;
+    }
+    // fused-path tables: orphan target bins (fed by no resolution) are written as zero by resolution 0
+    for (int r = 0; r < d->n_res; ++r) {
+        ResInfo& ri = p->res[r];
+        int mn = 1 << 30, mx = -1;
+        for (int l : lo[r]) { if (l < mn) mn = l; if (l > mx) mx = l; }
+        if (mx >= 0) { ri.need_lo = mn; ri.need_cnt = mx + 2 - mn; } else { ri.need_lo = 0; ri.need_cnt = 0; }
+        if (r == 0)
+            for (int t = 0; t < d->target_bins; ++t)
+                if (owners[t] == 0) { idx[0].push_back(t); lo[0].push_back(-1); fr[0].push_back(0.f); }
+        ri.n_tb = (int)idx[r].size();
+        int rc = upload((void**)&ri.tb_idx, idx[r].data(), idx[r].size() * sizeof(int)); if (rc) return rc;
+        rc = upload((void**)&ri.tb_lo, lo[r].data(), lo[r].size() * sizeof(int)); if (rc) return rc;
+        rc = upload((void**)&ri.tb_frac, fr[r].data(), fr[r].size() * sizeof(float)); if (rc) return rc;
+    }
+    // meters
+    int rc = upload((void**)&p->hann64, d->meter_hann, (size_t)p->W * sizeof(double)); if (rc) return rc;
+    std::vector<float> h32(p->W);
+    for (int i = 0; i < p->W; ++i) h32[i] = (float)d->meter_hann[i];
+    rc = upload((void**)&p->hann32, h32.data(), h32.size() * sizeof(float)); if (rc) return rc;
+    build_biquad(d->kw_coeffs + 0, d->kw_coeffs + 3, &p->kw[0]);
+    build_biquad(d->kw_coeffs + 6, d->kw_coeffs + 9, &p->kw[1]);
+    rc = get_twiddles(p->device, ilog2(p->W) - 1, &p->tw_meter); if (rc) return rc;
+    return OMEGA4_OK;
+}
+
+extern "C" omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int device) {
+    if (!desc) { fail(OMEGA4_ERR_INVALID, "desc is NULL"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(OMEGA4_ERR_INVALID, "bad device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(OMEGA4_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    omega4_plan* p = new omega4_plan();
+    p->device = device;
+    if (plan_build(p, desc) != OMEGA4_OK) { std::string keep = g_err; omega4_plan_destroy(p); g_err = keep; return nullptr; }
+    return p;
+}
+
+extern "C" void omega4_plan_destroy(omega4_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (int r = 0; r < OMEGA4_MAX_RES; ++r) {
+        ResInfo& ri = p->res[r];
+        cudaFree(ri.window); cudaFree(ri.binw); cudaFree(ri.tb_idx); cudaFree(ri.tb_lo); cudaFree(ri.tb_frac);
+        p->scratch_mag[r].release(); p->h_mag[r].release();
+    }
+    cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
+    cudaFree(p->hann64); cudaFree(p->hann32);
+    p->scratch_lufs.release(); p->scratch_tp.release();
+    p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
+    p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
+    for (auto& t : p->times) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    cudaGetLastError();
+    delete p;
+}
+
+extern "C" long long omega4_plan_launches(const omega4_plan* p) { return p ? p->launches : 0; }
+
+// event bracket helper
+struct Bracket {
+    omega4_plan* p; cudaStream_t s; bool on; KernelTime* kt = nullptr;
+    Bracket(omega4_plan* p_, cudaStream_t s_, bool on_, const char* name) : p(p_), s(s_), on(on_) {
+        p->launches++;
+        if (!on) return;
+        if (p->n_times == p->times.size()) {
+            KernelTime t; memset(&t, 0, sizeof t);
+            cudaEventCreate(&t.e0); cudaEventCreate(&t.e1);
+            p->times.push_back(t);
+        }
+        kt = &p->times[p->n_times++];
+        snprintf(kt->name, sizeof kt->name, "%s", name);
+        cudaEventRecord(kt->e0, s);
+    }
+    ~Bracket() { if (on && kt) cudaEventRecord(kt->e1, s); }
+};
+
+extern "C" int omega4_plan_kernel_times(omega4_plan* p, char* names, float* ms, int max_n) {
+    if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
+    int n = 0;
+    for (size_t i = 0; i < p->n_times && n < max_n; ++i, ++n) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, p->times[i].e0, p->times[i].e1) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+        if (names) { memcpy(names + 32 * n, p->times[i].name, 32); }
+        if (ms) ms[n] = t;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// the hot path on device pointers
+// ------------------------------------------------------------------------------------------
+static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long long ch_stride, int n_ch,
+                          int n_hops, int hist, float* combined, float* const* mags, float* meters,
+                          double* lufs, double* tp, double* state, int flags) {
+    const bool timing = (flags & OMEGA4_FLAG_TIME_KERNELS) != 0;
+    if (timing) p->n_times = 0;
+    if (((uintptr_t)x & 15) != 0 || (ch_stride % 4) != 0)
+        return fail(OMEGA4_ERR_INVALID, "samples must be 16-byte aligned with ch_stride a multiple of 4");
+    const bool fused = p->disjoint;
+    float* mag_ptr[OMEGA4_MAX_RES];
+    int first[OMEGA4_MAX_RES];
+    for (int r = 0; r < p->n_res; ++r) {
+        ResInfo& ri = p->res[r];
+        // resolution r is filled once hist + (k+1) hop >= N
+        long long need = (long long)ri.n - hist;
+        first[r] = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
+        mag_ptr[r] = mags ? mags[r] : nullptr;
+        if (combined && !fused && !mag_ptr[r]) {
+            int rc = p->scratch_mag[r].ensure((size_t)n_ch * n_hops * ri.bins * sizeof(float));
+            if (rc) return rc;
+            mag_ptr[r] = (float*)p->scratch_mag[r].p;
+        }
+        if (!combined && !mag_ptr[r]) continue;
+        MultiresArgs a;
+        memset(&a, 0, sizeof a);
+        a.x = x; a.ch_stride = ch_stride; a.frame_stride = p->hop; a.frame_off0 = (long long)p->hop - ri.n;
+        a.n_ch = n_ch; a.n_frames = n_hops; a.first_frame = first[r];
+        a.rounds = default_rounds(n_hops, (1 << ri.log2m) >= 4096 ? 1 : 4096 >> ri.log2m);
+        a.window = ri.window; a.binw = ri.binw; a.twM = ri.tw.twM; a.twN = ri.tw.twN;
+        a.mag_out = mag_ptr[r]; a.cplx_out = nullptr;
+        a.comb_out = (combined && fused) ? combined : nullptr;
+        a.T = p->T; a.n_tb = ri.n_tb; a.tb_idx = ri.tb_idx; a.tb_lo = ri.tb_lo; a.tb_frac = ri.tb_frac;
+        a.wnum = ri.weight; a.wden = ri.weight;
+        a.need_lo = ri.need_lo; a.need_cnt = (combined && fused) ? ri.need_cnt : 0;
+        char name[32];
+        snprintf(name, sizeof name, "multires_fft_%d", ri.n);
+        Bracket b(p, s, timing, name);
+        int rc = launch_multires(ri.log2m, a, s);
+        if (rc) return rc;
+    }
+    if (combined && !fused) {
+        CombineArgs c;
+        memset(&c, 0, sizeof c);
+        for (int r = 0; r < p->n_res; ++r) {
+            c.mag[r] = mag_ptr[r]; c.bins[r] = p->res[r].bins; c.first_frame[r] = first[r]; c.weight[r] = p->res[r].weight;
+        }
+        c.n_hops = n_hops; c.n_rows = n_ch * n_hops; c.T = p->T;
+        c.csr_ptr = p->csr_ptr; c.csr_res = p->csr_res; c.csr_lo = p->csr_lo; c.csr_frac = p->csr_frac;
+        c.out = combined;
+        const long long total = (long long)c.n_rows * c.T;
+        Bracket b(p, s, timing, "combine");
+        combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c);
+        CK(cudaGetLastError());
+    }
+    if (meters || lufs || tp) {
+        const size_t nser = (size_t)n_ch * n_hops * sizeof(double);
+        if (!lufs) { int rc = p->scratch_lufs.ensure(nser); if (rc) return rc; lufs = (double*)p->scratch_lufs.p; }
+        if (!tp) { int rc = p->scratch_tp.ensure(nser); if (rc) return rc; tp = (double*)p->scratch_tp.p; }
+        long long need = (long long)p->W - hist;
+        const int first_m = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
+        {
+            KweightArgs k;
+            memset(&k, 0, sizeof k);
+            k.x = x; k.x_is_f64 = 0; k.ch_stride = ch_stride; k.frame_stride = p->hop;
+            k.frame_off0 = (long long)p->hop - p->W;
+            k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
+            k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
+            k.hann = p->hann64; k.lufs_out = lufs; k.weighted_out = nullptr;
+            k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
+            Bracket b(p, s, timing, "kweight_lufs");
+            int rc = launch_kweight(k, s);
+            if (rc) return rc;
+        }
+        {
+            TruePeakArgs t;
+            memset(&t, 0, sizeof t);
+            t.x = x; t.x_is_f64 = 0; t.ch_stride = ch_stride; t.frame_stride = p->hop;
+            t.frame_off0 = (long long)p->hop - p->W;
+            t.n_ch = n_ch; t.n_frames = n_hops; t.first_frame = first_m;
+            t.rounds = default_rounds(n_hops, 4);
+            t.window = p->hann32; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
+            t.tp_out = tp;
+            Bracket b(p, s, timing, "true_peak");
+            int rc = launch_truepeak(t, s);
+            if (rc) return rc;
+        }
+        if (meters) {
+            StatsArgs st;
+            memset(&st, 0, sizeof st);
+            st.lufs = lufs; st.tp = tp; st.n_ch = n_ch; st.n_frames = n_hops; st.first_frame = first_m;
+            st.gate = p->gate; st.out = meters;
+            st.fresh = (state == nullptr) || (flags & OMEGA4_FLAG_FRESH_METERS) ? 1 : 0;
+            if (!state) {
+                int rc = p->h_state.ensure((size_t)n_ch * ST_STATE * sizeof(double));
+                if (rc) return rc;
+                state = (double*)p->h_state.p;
+            }
+            st.state = state;
+            Bracket b(p, s, timing, "meter_stats");
+            int rc = launch_stats(st, s);
+            if (rc) return rc;
+        }
+    }
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float* samples, long long ch_stride,
+                              int n_ch, int n_hops, int hist_samples, float* combined, float* const* magnitudes,
+                              float* meters, double* lufs_inst, double* tp_db, double* meter_state, int flags) {
+    if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
+    if (!samples || n_ch < 0 || n_hops < 0 || hist_samples < 0) return fail(OMEGA4_ERR_INVALID, "bad samples / sizes");
+    if (n_ch == 0 || n_hops == 0) return OMEGA4_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mem == OMEGA4_MEM_DEVICE)
+        return analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
+                              lufs_inst, tp_db, meter_state, flags);
+    if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
+
+    // ---- host buffers: stage, run, copy back (synchronous)
+    const long long hist = hist_samples;
+    const long long hist_al = (hist + 3) / 4 * 4;                 // keep rows 16-byte aligned
+    const long long row_len = hist_al + (long long)n_hops * p->hop;
+    const long long dstride = (row_len + 3) / 4 * 4;
+    int rc = p->h_in.ensure((size_t)n_ch * dstride * sizeof(float));
+    if (rc) return rc;
+    float* d_in = (float*)p->h_in.p;
+    // device row c = [pad (hist_al - hist) | hist samples | n_hops*hop samples]
+    CK(cudaMemcpy2DAsync(d_in + (hist_al - hist), dstride * sizeof(float), samples - hist, ch_stride * sizeof(float),
+                         (size_t)(hist + (long long)n_hops * p->hop) * sizeof(float), n_ch, cudaMemcpyHostToDevice, s));
+    float* d_comb = nullptr; float* d_met = nullptr; double* d_state = nullptr;
+    double* d_lufs = nullptr; double* d_tp = nullptr;
+    float* d_mag[OMEGA4_MAX_RES] = {nullptr};
+    const size_t rows = (size_t)n_ch * n_hops;
+    if (combined) { rc = p->h_comb.ensure(rows * p->T * sizeof(float)); if (rc) return rc; d_comb = (float*)p->h_comb.p; }
+    if (meters) { rc = p->h_meters.ensure(rows * 5 * sizeof(float)); if (rc) return rc; d_met = (float*)p->h_meters.p; }
+    if (lufs_inst) { rc = p->h_f64a.ensure(rows * sizeof(double)); if (rc) return rc; d_lufs = (double*)p->h_f64a.p; }
+    if (tp_db) { rc = p->h_f64b.ensure(rows * sizeof(double)); if (rc) return rc; d_tp = (double*)p->h_f64b.p; }
+    if (meter_state) {
+        rc = p->h_f64c.ensure((size_t)n_ch * ST_STATE * sizeof(double)); if (rc) return rc;
+        d_state = (double*)p->h_f64c.p;
+        CK(cudaMemcpyAsync(d_state, meter_state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    bool any_mag = false;
+    if (magnitudes)
+        for (int r = 0; r < p->n_res; ++r)
+            if (magnitudes[r]) {
+                rc = p->h_mag[r].ensure(rows * p->res[r].bins * sizeof(float)); if (rc) return rc;
+                d_mag[r] = (float*)p->h_mag[r].p; any_mag = true;
+            }
+    rc = analyze_device(p, s, d_in + hist_al, dstride, n_ch, n_hops, (int)hist,
+                        d_comb, any_mag ? d_mag : nullptr, d_met, d_lufs, d_tp, d_state, flags);
+    if (rc) return rc;
+    if (combined) CK(cudaMemcpyAsync(combined, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (meters) CK(cudaMemcpyAsync(meters, d_met, rows * 5 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (lufs_inst) CK(cudaMemcpyAsync(lufs_inst, d_lufs, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (tp_db) CK(cudaMemcpyAsync(tp_db, d_tp, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (meter_state) CK(cudaMemcpyAsync(meter_state, d_state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (magnitudes)
+        for (int r = 0; r < p->n_res; ++r)
+            if (magnitudes[r]) CK(cudaMemcpyAsync(magnitudes[r], d_mag[r], rows * p->res[r].bins * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// combine on caller-supplied magnitudes
+// ------------------------------------------------------------------------------------------
+extern "C" int omega4_combine(omega4_plan* p, void* stream, int mem, const float* const* magnitudes, int n_rows,
+                              float* combined) {
+    if (!p || !magnitudes || !combined || n_rows < 0) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_rows == 0) return OMEGA4_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CombineArgs c;
+    memset(&c, 0, sizeof c);
+    float* d_out = combined;
+    if (mem == OMEGA4_MEM_HOST) {
+        for (int r = 0; r < p->n_res; ++r)
+            if (magnitudes[r]) {
+                const size_t bytes = (size_t)n_rows * p->res[r].bins * sizeof(float);
+                int rc = p->h_mag[r].ensure(bytes); if (rc) return rc;
+                CK(cudaMemcpyAsync(p->h_mag[r].p, magnitudes[r], bytes, cudaMemcpyHostToDevice, s));
+                c.mag[r] = (const float*)p->h_mag[r].p;
+            }
+        int rc = p->h_comb.ensure((size_t)n_rows * p->T * sizeof(float)); if (rc) return rc;
+        d_out = (float*)p->h_comb.p;
+    } else {
+        for (int r = 0; r < p->n_res; ++r) c.mag[r] = magnitudes[r];
+    }
+    for (int r = 0; r < p->n_res; ++r) { c.bins[r] = p->res[r].bins; c.first_frame[r] = 0; c.weight[r] = p->res[r].weight; }
+    c.n_hops = 0; c.n_rows = n_rows; c.T = p->T;
+    c.csr_ptr = p->csr_ptr; c.csr_res = p->csr_res; c.csr_lo = p->csr_lo; c.csr_frac = p->csr_frac;
+    c.out = d_out;
+    const long long total = (long long)n_rows * p->T;
+    p->launches++;
+    combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c);
+    CK(cudaGetLastError());
+    if (mem == OMEGA4_MEM_HOST) {
+        CK(cudaMemcpyAsync(combined, d_out, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// meters on explicit frames / series
+// ------------------------------------------------------------------------------------------
+extern "C" int omega4_meter_frames(omega4_plan* p, void* stream, int mem, const double* frames, int n_frames,
+                                   double* lufs_inst, double* tp_db, double* weighted) {
+    if (!p || !frames || n_frames < 0) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_frames == 0) return OMEGA4_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int W = p->W;
+    const double* d_fr = frames; double* d_l = lufs_inst; double* d_t = tp_db; double* d_w = weighted;
+    DevBuf tmp_w;
+    if (mem == OMEGA4_MEM_HOST) {
+        int rc = p->h_f64a.ensure((size_t)n_frames * W * sizeof(double)); if (rc) return rc;
+        CK(cudaMemcpyAsync(p->h_f64a.p, frames, (size_t)n_frames * W * sizeof(double), cudaMemcpyHostToDevice, s));
+        d_fr = (const double*)p->h_f64a.p;
+        rc = p->h_f64b.ensure((size_t)n_frames * 2 * sizeof(double)); if (rc) return rc;
+        d_l = (double*)p->h_f64b.p; d_t = d_l + n_frames;
+        if (weighted) { rc = tmp_w.ensure((size_t)n_frames * W * sizeof(double)); if (rc) return rc; d_w = (double*)tmp_w.p; }
+    } else if (((uintptr_t)frames & 15) != 0) {
+        return fail(OMEGA4_ERR_INVALID, "frames must be 16-byte aligned");
+    }
+    int rc = OMEGA4_OK;
+    if (lufs_inst || weighted) {
+        if (!d_l || (mem == OMEGA4_MEM_DEVICE && !lufs_inst)) { rc = p->scratch_lufs.ensure((size_t)n_frames * sizeof(double)); if (rc) { tmp_w.release(); return rc; } d_l = (double*)p->scratch_lufs.p; }
+        KweightArgs k;
+        memset(&k, 0, sizeof k);
+        k.x = d_fr; k.x_is_f64 = 1; k.ch_stride = 0; k.frame_stride = W; k.frame_off0 = 0;
+        k.n_ch = 1; k.n_frames = n_frames; k.first_frame = 0; k.frames_per_warp = n_frames >= 64 ? 4 : 1;
+        k.hann = nullptr; k.lufs_out = d_l; k.weighted_out = d_w;
+        k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
+        p->launches++;
+        rc = launch_kweight(k, s);
+        if (rc) { tmp_w.release(); return rc; }
+    }
+    if (tp_db) {
+        TruePeakArgs t;
+        memset(&t, 0, sizeof t);
+        t.x = d_fr; t.x_is_f64 = 1; t.ch_stride = 0; t.frame_stride = W; t.frame_off0 = 0;
+        t.n_ch = 1; t.n_frames = n_frames; t.first_frame = 0; t.rounds = default_rounds(n_frames, 4);
+        t.window = nullptr; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
+        t.tp_out = d_t;
+        p->launches++;
+        rc = launch_truepeak(t, s);
+        if (rc) { tmp_w.release(); return rc; }
+    }
+    if (mem == OMEGA4_MEM_HOST) {
+        cudaError_t e = cudaSuccess;
+        if (lufs_inst) e = cudaMemcpyAsync(lufs_inst, d_l, (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && tp_db) e = cudaMemcpyAsync(tp_db, d_t, (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && weighted) e = cudaMemcpyAsync(weighted, d_w, (size_t)n_frames * W * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        tmp_w.release();
+        if (e != cudaSuccess) return fail(OMEGA4_ERR_CUDA, std::string("meter_frames copy back failed: ") + cudaGetErrorString(e));
+    }
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_meter_stats(omega4_plan* p, void* stream, int mem, const double* lufs_inst, const double* tp_db,
+                                  int n_ch, int n_frames, int first_frame, double* state, float* meters, int fresh) {
+    if (!p || !lufs_inst || !tp_db || !meters || n_ch < 0 || n_frames < 0) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_ch == 0 || n_frames == 0) return OMEGA4_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    StatsArgs st;
+    memset(&st, 0, sizeof st);
+    const size_t rows = (size_t)n_ch * n_frames;
+    st.n_ch = n_ch; st.n_frames = n_frames; st.first_frame = first_frame; st.gate = p->gate; st.fresh = fresh ? 1 : 0;
+    if (mem == OMEGA4_MEM_HOST) {
+        int rc = p->h_f64a.ensure(rows * 2 * sizeof(double)); if (rc) return rc;
+        double* d = (double*)p->h_f64a.p;
+        CK(cudaMemcpyAsync(d, lufs_inst, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d + rows, tp_db, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+        st.lufs = d; st.tp = d + rows;
+        rc = p->h_f64c.ensure((size_t)n_ch * ST_STATE * sizeof(double)); if (rc) return rc;
+        st.state = (double*)p->h_f64c.p;
+        if (state && !fresh) CK(cudaMemcpyAsync(st.state, state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyHostToDevice, s));
+        else st.fresh = 1;
+        rc = p->h_meters.ensure(rows * 5 * sizeof(float)); if (rc) return rc;
+        st.out = (float*)p->h_meters.p;
+    } else {
+        st.lufs = lufs_inst; st.tp = tp_db; st.out = meters;
+        if (state) st.state = state;
+        else { int rc = p->h_state.ensure((size_t)n_ch * ST_STATE * sizeof(double)); if (rc) return rc; st.state = (double*)p->h_state.p; st.fresh = 1; }
+    }
+    p->launches++;
+    int rc = launch_stats(st, s);
+    if (rc) return rc;
+    if (mem == OMEGA4_MEM_HOST) {
+        CK(cudaMemcpyAsync(meters, st.out, rows * 5 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (state) CK(cudaMemcpyAsync(state, st.state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan-less entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int omega4_rfft_batch(int device, void* stream, int mem, const float* frames, int batch, int n,
+                                 const float* window, float* magnitude, float* complex_out) {
+    if (!frames || batch < 0 || (!magnitude && !complex_out)) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (!is_pow2(n) || n < 512 || n > 32768) return fail(OMEGA4_ERR_UNSUPPORTED, "fft size must be a power of two in 512 .. 32768");
+    if (batch == 0) return OMEGA4_OK;
+    if (omega4_device_count() == 0) return fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int log2m = ilog2(n) - 1, bins = n / 2 + 1;
+    Twiddles tw;
+    int rc = get_twiddles(device, log2m, &tw);
+    if (rc) return rc;
+    float* d_win = nullptr; float* d_in = nullptr; float* d_mag = nullptr; float2* d_c = nullptr;
+    std::vector<void*> to_free;
+    auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
+#define CKF(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(OMEGA4_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(e__)); } } while (0)
+    if (window) {
+        CKF(cudaMalloc(&d_win, (size_t)n * sizeof(float))); to_free.push_back(d_win);
+        CKF(cudaMemcpyAsync(d_win, window, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (mem == OMEGA4_MEM_HOST) {
+        CKF(cudaMalloc(&d_in, (size_t)batch * n * sizeof(float))); to_free.push_back(d_in);
+        CKF(cudaMemcpyAsync(d_in, frames, (size_t)batch * n * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (magnitude) { CKF(cudaMalloc(&d_mag, (size_t)batch * bins * sizeof(float))); to_free.push_back(d_mag); }
+        if (complex_out) { CKF(cudaMalloc(&d_c, (size_t)batch * bins * sizeof(float2))); to_free.push_back(d_c); }
+    } else {
+        if (((uintptr_t)frames & 15) != 0) { cleanup(); return fail(OMEGA4_ERR_INVALID, "frames must be 16-byte aligned"); }
+        d_in = const_cast<float*>(frames); d_mag = magnitude; d_c = reinterpret_cast<float2*>(complex_out);
+    }
+    MultiresArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = d_in; a.ch_stride = 0; a.frame_stride = n; a.frame_off0 = 0;
+    a.n_ch = 1; a.n_frames = batch; a.first_frame = 0;
+    a.rounds = default_rounds(batch, (1 << log2m) >= 4096 ? 1 : 4096 >> log2m);
+    a.window = d_win; a.binw = nullptr; a.twM = tw.twM; a.twN = tw.twN;
+    a.mag_out = d_mag; a.cplx_out = d_c; a.comb_out = nullptr; a.T = 0; a.n_tb = 0; a.need_lo = 0; a.need_cnt = 0;
+    rc = launch_multires(log2m, a, s);
+    if (rc) { cleanup(); return rc; }
+    if (mem == OMEGA4_MEM_HOST) {
+        if (magnitude) CKF(cudaMemcpyAsync(magnitude, d_mag, (size_t)batch * bins * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (complex_out) CKF(cudaMemcpyAsync(complex_out, d_c, (size_t)batch * bins * sizeof(float2), cudaMemcpyDeviceToHost, s));
+    }
+    if (!to_free.empty()) CKF(cudaStreamSynchronize(s));
+    cleanup();
+#undef CKF
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_band_map(int device, void* stream, int mem, const float* spectrum, int n_rows, int len,
+                               const int* bands, int n_bars, const float* comp, float* bars_out, int db) {
+    if (!spectrum || !bands || !bars_out || n_rows < 0 || len <= 0 || n_bars <= 0) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_rows == 0) return OMEGA4_OK;
+    if (omega4_device_count() == 0) return fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int n_valid = n_bars;
+    for (int b = 0; b < n_bars; ++b) {
+        if (bands[2 * b] < 0 || bands[2 * b + 1] < bands[2 * b]) return fail(OMEGA4_ERR_INVALID, "bad band table");
+        if (bands[2 * b + 1] > len) { n_valid = b; break; }        // freq_mapper.py:188-189 `break`
+    }
+    std::vector<void*> to_free;
+    auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
+#define CKF(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(OMEGA4_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(e__)); } } while (0)
+    int* d_bands = nullptr; float* d_comp = nullptr; const float* d_spec = spectrum; float* d_out = bars_out;
+    CKF(cudaMalloc(&d_bands, (size_t)n_bars * 2 * sizeof(int))); to_free.push_back(d_bands);
+    CKF(cudaMemcpyAsync(d_bands, bands, (size_t)n_bars * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (comp) {
+        CKF(cudaMalloc(&d_comp, (size_t)len * sizeof(float))); to_free.push_back(d_comp);
+        CKF(cudaMemcpyAsync(d_comp, comp, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (mem == OMEGA4_MEM_HOST) {
+        float* t = nullptr;
+        CKF(cudaMalloc(&t, (size_t)n_rows * len * sizeof(float))); to_free.push_back(t);
+        CKF(cudaMemcpyAsync(t, spectrum, (size_t)n_rows * len * sizeof(float), cudaMemcpyHostToDevice, s));
+        d_spec = t;
+        CKF(cudaMalloc(&d_out, (size_t)n_rows * n_bars * sizeof(float))); to_free.push_back(d_out);
+    }
+    const long long total = (long long)n_rows * n_bars;
+    band_map_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_spec, n_rows, len, d_bands, n_bars, n_valid, d_comp, d_out, db);
+    CKF(cudaGetLastError());
+    if (mem == OMEGA4_MEM_HOST) CKF(cudaMemcpyAsync(bars_out, d_out, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CKF(cudaStreamSynchronize(s));
+    cleanup();
+#undef CKF
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams, int n_channels,
+                                 long long n_samples, long long row_stride, int first_stream, int sample_rate,
+                                 long long clip_samples) {
+    if (!out_device || n_streams < 0 || n_channels <= 0 || n_samples < 0 || row_stride < n_samples || sample_rate <= 0)
+        return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_streams == 0 || n_samples == 0) return OMEGA4_OK;
+    if (omega4_device_count() == 0) return fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const int rows = n_streams * n_channels;
+    if (rows > 65535) return fail(OMEGA4_ERR_INVALID, "too many rows for one synth launch (max 65535)");
+    const double clip_s = (double)(clip_samples > 0 ? clip_samples : n_samples) / sample_rate;
+    dim3 grid((unsigned)((n_samples + 255) / 256), rows);
+    synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_device, rows, n_channels, n_samples, row_stride, first_stream,
+                                                         (double)sample_rate, clip_s);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}

@@ -1,0 +1,146 @@
+"""ctypes binding of libomega4_cuda.so (C ABI: include/omega4_cuda.h).
+
+There is no CPU fallback anywhere in this package: if the library is missing, cannot be loaded
+or reports no CUDA device, the call raises ``Omega4CudaError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+
+LIB_NAME = "libomega4_cuda.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+OK = 0
+MEM_HOST = 0
+MEM_DEVICE = 1
+MAX_RES = 8
+METER_WINDOW = 2048
+METER_STATE_DOUBLES = 8 + 3600 + 60
+N_METERS = 5
+FLAG_TIME_KERNELS = 1
+FLAG_FRESH_METERS = 2
+ABI_VERSION = 1
+
+#: every symbol include/omega4_cuda.h declares (checked by tests/test_abi_symbols.py)
+EXPORTS = (
+    "omega4_abi_version", "omega4_last_error", "omega4_device_count",
+    "omega4_plan_create", "omega4_plan_destroy", "omega4_analyze", "omega4_combine",
+    "omega4_meter_frames", "omega4_meter_stats", "omega4_rfft_batch", "omega4_band_map",
+    "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
+)
+
+
+class Omega4CudaError(RuntimeError):
+    pass
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int), ("hop", C.c_int), ("n_res", C.c_int),
+        ("fft_sizes", C.POINTER(C.c_int)),
+        ("windows", C.POINTER(C.c_float)),
+        ("bin_weights", C.POINTER(C.c_float)),
+        ("target_bins", C.c_int),
+        ("tb_count", C.POINTER(C.c_int)),
+        ("tb_idx", C.POINTER(C.c_int)),
+        ("tb_lo", C.POINTER(C.c_int)),
+        ("tb_frac", C.POINTER(C.c_float)),
+        ("res_weight", C.POINTER(C.c_float)),
+        ("meter_window", C.c_int),
+        ("meter_hann", C.POINTER(C.c_double)),
+        ("kw_coeffs", C.POINTER(C.c_double)),
+        ("gate_threshold", C.c_double),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the library; raises Omega4CudaError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise Omega4CudaError(
+                f"{LIB_PATH} is missing -- build it with `python audio-analyzer-omega_b200/build.py` "
+                "(nvcc, sm_100a). omega4_b200 has no CPU fallback.")
+        try:
+            l = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise Omega4CudaError(f"cannot load {LIB_PATH}: {e}") from e
+        vp, ip, ll = C.c_void_p, C.c_int, C.c_longlong
+        l.omega4_abi_version.restype = ip
+        l.omega4_last_error.restype = C.c_char_p
+        l.omega4_device_count.restype = ip
+        l.omega4_plan_create.restype = vp
+        l.omega4_plan_create.argtypes = [C.POINTER(PlanDesc), ip]
+        l.omega4_plan_destroy.restype = None
+        l.omega4_plan_destroy.argtypes = [vp]
+        l.omega4_analyze.restype = ip
+        l.omega4_analyze.argtypes = [vp, vp, ip, vp, ll, ip, ip, ip, vp, C.POINTER(vp), vp, vp, vp, vp, ip]
+        l.omega4_combine.restype = ip
+        l.omega4_combine.argtypes = [vp, vp, ip, C.POINTER(vp), ip, vp]
+        l.omega4_meter_frames.restype = ip
+        l.omega4_meter_frames.argtypes = [vp, vp, ip, vp, ip, vp, vp, vp]
+        l.omega4_meter_stats.restype = ip
+        l.omega4_meter_stats.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip]
+        l.omega4_rfft_batch.restype = ip
+        l.omega4_rfft_batch.argtypes = [ip, vp, ip, vp, ip, ip, vp, vp, vp]
+        l.omega4_band_map.restype = ip
+        l.omega4_band_map.argtypes = [ip, vp, ip, vp, ip, ip, vp, ip, vp, vp, ip]
+        l.omega4_synth_fill.restype = ip
+        l.omega4_synth_fill.argtypes = [ip, vp, vp, ip, ip, ll, ll, ip, ip, ll]
+        l.omega4_plan_launches.restype = ll
+        l.omega4_plan_launches.argtypes = [vp]
+        l.omega4_plan_kernel_times.restype = ip
+        l.omega4_plan_kernel_times.argtypes = [vp, vp, vp, ip]
+        if l.omega4_abi_version() != ABI_VERSION:
+            raise Omega4CudaError(f"{LIB_NAME} ABI {l.omega4_abi_version()} != binding ABI {ABI_VERSION}")
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().omega4_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "omega4_cuda") -> None:
+    if rc != OK:
+        raise Omega4CudaError(f"{what} failed ({rc}): {last_error()}")
+
+
+def require_device() -> int:
+    n = lib().omega4_device_count()
+    if n < 1:
+        raise Omega4CudaError("no CUDA device visible: omega4_b200 has no CPU fallback")
+    return n
+
+
+def ptr(a) -> Optional[int]:
+    """Address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    if isinstance(a, int):
+        return a
+    raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def ptr_array(items: Sequence) -> "C.Array":
+    arr = (C.c_void_p * len(items))()
+    for i, it in enumerate(items):
+        arr[i] = ptr(it)
+    return arr

@@ -1,0 +1,143 @@
+/* omega4_cuda.h -- C ABI of libomega4_cuda.so: the B200 (sm_100a) implementation of OMEGA-4's
+ * per-frame analysis hot path.  Plain C linkage, plain pointers and sizes, no C++/torch types.
+ *
+ * The reference (magicat777/Audio-Analyzer-OMEGA) is 100 % Python and has no FFI; its boundary for
+ * this path is a set of Python classes.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root); the thin Python shims in
+ * audio-analyzer-omega_b200/omega4_b200/ keep those classes' signatures and call these functions
+ * through ctypes (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns OMEGA4_OK (0) or a negative error code; omega4_last_error() returns a
+ *     thread-local message for the last failure.  Nothing here falls back to the CPU.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *     asynchronous on that stream in OMEGA4_MEM_DEVICE mode and synchronous in OMEGA4_MEM_HOST mode.
+ *   - `mem` says where the DATA pointers of that call live (samples, frames, outputs).  Table
+ *     pointers in omega4_plan_desc are always host memory and are copied at plan creation.
+ *   - sample/frame pointers must be 16-byte aligned in device mode.
+ */
+#ifndef OMEGA4_CUDA_H
+#define OMEGA4_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMEGA4_ABI_VERSION 1
+
+#define OMEGA4_OK 0
+#define OMEGA4_ERR_INVALID (-1)   /* bad argument */
+#define OMEGA4_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define OMEGA4_ERR_UNSUPPORTED (-3)
+#define OMEGA4_ERR_NO_DEVICE (-4)
+
+#define OMEGA4_MEM_HOST 0
+#define OMEGA4_MEM_DEVICE 1
+
+#define OMEGA4_MAX_RES 8
+#define OMEGA4_METER_WINDOW 2048                 /* FFT_SIZE_BASE, omega4/config/config.py:12 */
+#define OMEGA4_METER_STATE_DOUBLES (8 + 3600 + 60) /* carry state per channel for omega4_meter_stats */
+#define OMEGA4_N_METERS 5                        /* momentary, short_term, integrated, range, true_peak */
+
+/* omega4_analyze flags */
+#define OMEGA4_FLAG_TIME_KERNELS 1               /* record CUDA events around every kernel launch */
+#define OMEGA4_FLAG_FRESH_METERS 2               /* ignore meter_state contents on entry */
+
+typedef struct omega4_plan omega4_plan;
+
+/* Everything that defines the reference's behaviour is DATA computed on the host with the
+ * reference's own formulas and handed over here. */
+typedef struct omega4_plan_desc {
+    int sample_rate;
+    int hop;                       /* CHUNK_SIZE = 512 */
+    int n_res;                     /* number of FFT resolutions, <= OMEGA4_MAX_RES */
+    const int* fft_sizes;          /* [n_res] powers of two in 512 .. 32768 */
+    const float* windows;          /* concatenated float32 windows, sum(fft_sizes) entries
+                                      (MultiResolutionFFT._setup_windows, multi_resolution_fft.py:171-193) */
+    const float* bin_weights;      /* concatenated per-bin weights, sum(fft_size/2+1) entries, or NULL
+                                      (_apply_psychoacoustic_weighting, :304-333) */
+    int target_bins;               /* T of combine_results_optimized (:335) */
+    const int* tb_count;           /* [n_res] target bins fed by each resolution */
+    const int* tb_idx;             /* concatenated target-bin indices */
+    const int* tb_lo;              /* concatenated lower FFT-bin index of the np.interp segment */
+    const float* tb_frac;          /* concatenated interpolation fractions */
+    const float* res_weight;       /* [n_res] FFTConfig.weight (:149-154) */
+    int meter_window;              /* must be OMEGA4_METER_WINDOW */
+    const double* meter_hann;      /* [meter_window] float64 np.hanning (omega4_main.py:953) */
+    const double* kw_coeffs;       /* hp_b[3] hp_a[3] shelf_b[3] shelf_a[3]
+                                      (create_k_weighting_filter, professional_meters.py:48-72) */
+    double gate_threshold;         /* -70.0 (:36) */
+} omega4_plan_desc;
+
+int omega4_abi_version(void);
+const char* omega4_last_error(void);
+int omega4_device_count(void);
+
+/* ---- plan ------------------------------------------------------------------------------- */
+omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int device);
+void omega4_plan_destroy(omega4_plan* plan);
+
+/* The whole hot path over a batch: replaces, per channel and hop,
+ *   MultiResolutionFFT.process_audio_chunk + combine_results_optimized (multi_resolution_fft.py:228,335)
+ *   ProfessionalMetering.calculate_lufs on the Hann-windowed last 2048 samples (professional_meters.py:231)
+ * as the caller omega4_main.py:928-1082 drives them, on the shared schedule of SURVEY.md section 7:
+ * hop k of a channel ends at sample (k+1)*hop; resolution N contributes once hist_samples+(k+1)*hop >= N.
+ *   samples        [n_ch] rows, row c starts at samples + c*ch_stride; `hist_samples` valid samples
+ *                  precede each row start (carry of a previous time tile), 0 for a fresh stream
+ *   combined       [n_ch][n_hops][target_bins] float32, or NULL
+ *   magnitudes     [n_res] pointers (entries may be NULL) to [n_ch][n_hops][N/2+1] float32, or NULL
+ *   meters         [n_ch][n_hops][5] float32 (M, S, I, LRA, TP), or NULL
+ *   lufs_inst/tp_db [n_ch][n_hops] float64 per-frame values, or NULL (internal scratch is used)
+ *   meter_state    [n_ch][OMEGA4_METER_STATE_DOUBLES] carried deque state, or NULL (fresh meters) */
+int omega4_analyze(omega4_plan* plan, void* stream, int mem,
+                   const float* samples, long long ch_stride, int n_ch, int n_hops, int hist_samples,
+                   float* combined, float* const* magnitudes, float* meters,
+                   double* lufs_inst, double* tp_db, double* meter_state, int flags);
+
+/* combine_results_optimized (multi_resolution_fft.py:335-408) on caller-supplied magnitudes:
+ * magnitudes[r] = [n_rows][N_r/2+1] or NULL when resolution r is absent from `results`. */
+int omega4_combine(omega4_plan* plan, void* stream, int mem,
+                   const float* const* magnitudes, int n_rows, float* combined);
+
+/* ProfessionalMetering on explicit float64 frames of OMEGA4_METER_WINDOW samples
+ * (apply_k_weighting :129, calculate_lufs :237-246, calculate_true_peak :283).
+ * lufs_inst / tp_db: [n_frames]; weighted: [n_frames][W] K-weighted frames or NULL. */
+int omega4_meter_frames(omega4_plan* plan, void* stream, int mem,
+                        const double* frames, int n_frames,
+                        double* lufs_inst, double* tp_db, double* weighted);
+
+/* The deque statistics of calculate_lufs (professional_meters.py:248-279) over per-frame series. */
+int omega4_meter_stats(omega4_plan* plan, void* stream, int mem,
+                       const double* lufs_inst, const double* tp_db, int n_ch, int n_frames,
+                       int first_frame, double* state, float* meters, int fresh);
+
+/* ---- plan-less entry points --------------------------------------------------------------- */
+/* Batched windowed rFFT + magnitude: BatchedFFTProcessor._process_size_group_{gpu,cpu}
+ * (batched_fft_processor.py:197-285) and GPUAcceleratedFFT.compute_fft / process_fft_batch
+ * (gpu_accelerated_fft.py:92-177, 300-340).  frames [batch][n] float32; window [n] HOST float32 or
+ * NULL; magnitude [batch][n/2+1]; complex_out interleaved (re,im) [batch][n/2+1][2] or NULL. */
+int omega4_rfft_batch(int device, void* stream, int mem, const float* frames, int batch, int n,
+                      const float* window, float* magnitude, float* complex_out);
+
+/* PrecomputedFrequencyMapper.map_spectrum_to_bars (freq_mapper.py:165-196): bar = mean(spectrum[s:e])
+ * with optional compensation curve; bands [n_bars][2] HOST int32; comp [len] HOST or NULL.
+ * db != 0 additionally converts 20*log10(max(x,1e-10)) (panels/spectrogram_waterfall.py:85). */
+int omega4_band_map(int device, void* stream, int mem, const float* spectrum, int n_rows, int len,
+                    const int* bands, int n_bars, const float* comp, float* bars_out, int db);
+
+/* Device-side synthetic multi-stream audio for the headless batch driver (sweep + counter-hash noise). */
+int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams, int n_channels,
+                      long long n_samples, long long row_stride, int first_stream, int sample_rate,
+                      long long clip_samples);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* number of kernels this library launched through `plan` since creation */
+long long omega4_plan_launches(const omega4_plan* plan);
+/* After an omega4_analyze(..., OMEGA4_FLAG_TIME_KERNELS) call has completed: per-kernel device
+ * times of that call.  names: array of max_n char[32] buffers.  Returns the number of kernels. */
+int omega4_plan_kernel_times(omega4_plan* plan, char* names, float* ms, int max_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMEGA4_CUDA_H */
