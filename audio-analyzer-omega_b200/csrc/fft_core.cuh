@@ -129,6 +129,10 @@ struct FftShape {
     static constexpr int NTW = (LOG2M - 1) / 4;   // number of twiddled radix-16 stages (n >= 32)
     static constexpr int TAIL = M >> (4 * (LOG2M / 4));          // 1, 2, 4 or 8
     static constexpr bool LAST16 = (LOG2M % 4 == 0);             // final untwiddled radix-16 stage
+    // two ping-pong buffers per sub-FFT, except for the largest size where 2 x 136 KB does not
+    // fit in shared memory: there the stages run in place with one extra barrier each.
+    static constexpr bool PINGPONG = (LOG2M <= 13);
+    static constexpr int NBUF = PINGPONG ? 2 : 1;
     static_assert(LOG2M >= 8 && LOG2M <= 14, "supported complex sizes: 256 .. 16384");
 };
 
@@ -180,8 +184,9 @@ __device__ __forceinline__ float2* fft_forward(float2* v, float2* buf0, float2* 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = src[rbase + j * RSTRIDE];
             }
+            if (!S::PINGPONG) __syncthreads();     // in place: everyone has read before anyone writes
         }
-        dst = (i & 1) ? buf1 : buf0;
+        dst = (S::PINGPONG && (i & 1)) ? buf1 : buf0;
         if (active) {
             bf16pt(v);
             apply_twiddles(v, st.t[i]);

@@ -44,13 +44,13 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
     constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufs = reinterpret_cast<float2*>(smem_raw);
-    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * 2 * BUF);
+    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * S::NBUF * BUF);
 
     const int tid = threadIdx.x;
     const int g = tid / TPF;
     const int t = tid % TPF;
-    float2* buf0 = bufs + (size_t)g * 2 * BUF;
-    float2* buf1 = buf0 + BUF;
+    float2* buf0 = bufs + (size_t)g * S::NBUF * BUF;
+    float2* buf1 = S::PINGPONG ? buf0 + BUF : buf0;
     float* mags = mags_all + (size_t)g * a.need_cnt;
 
     const int frames_per_cta = a.rounds * CONC;
@@ -155,7 +155,7 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
 template <int LOG2M>
 inline size_t multires_smem_bytes(int need_cnt) {
     using S = FftShape<LOG2M>;
-    return (size_t)S::CONC * 2 * S::BUF * sizeof(float2) + (size_t)S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float);
+    return (size_t)S::CONC * S::NBUF * S::BUF * sizeof(float2) + (size_t)S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float);
 }
 
 }  // namespace o4

@@ -239,6 +239,15 @@ struct omega4_plan {
     Twiddles tw_meter;
     DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES];
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
+    // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
+    // that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
+    struct Slot {
+        cudaStream_t s = nullptr;
+        DevBuf in, comb, met, lufs, tp, state, mag[OMEGA4_MAX_RES];
+    };
+    static constexpr int N_SLOTS = 3;
+    Slot slots[N_SLOTS];
+    size_t host_chunk_bytes = (size_t)768 << 20;   // device bytes per slot
     long long launches = 0;
     std::vector<KernelTime> times;
     size_t n_times = 0;
@@ -357,6 +366,11 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     p->scratch_lufs.release(); p->scratch_tp.release();
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
+    for (auto& sl : p->slots) {
+        sl.in.release(); sl.comb.release(); sl.met.release(); sl.lufs.release(); sl.tp.release(); sl.state.release();
+        for (auto& m : sl.mag) m.release();
+        if (sl.s) cudaStreamDestroy(sl.s);
+    }
     for (auto& t : p->times) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     cudaGetLastError();
     delete p;
@@ -515,49 +529,77 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
                               lufs_inst, tp_db, meter_state, flags);
     if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
 
-    // ---- host buffers: stage, run, copy back (synchronous)
+    // ---- host buffers: channel chunks pipelined over private streams (H2D | kernels | D2H overlap)
+    CK(cudaStreamSynchronize(s));                                  // order after the caller's stream
     const long long hist = hist_samples;
-    const long long hist_al = (hist + 3) / 4 * 4;                 // keep rows 16-byte aligned
-    const long long row_len = hist_al + (long long)n_hops * p->hop;
-    const long long dstride = (row_len + 3) / 4 * 4;
-    int rc = p->h_in.ensure((size_t)n_ch * dstride * sizeof(float));
-    if (rc) return rc;
-    float* d_in = (float*)p->h_in.p;
-    // device row c = [pad (hist_al - hist) | hist samples | n_hops*hop samples]
-    CK(cudaMemcpy2DAsync(d_in + (hist_al - hist), dstride * sizeof(float), samples - hist, ch_stride * sizeof(float),
-                         (size_t)(hist + (long long)n_hops * p->hop) * sizeof(float), n_ch, cudaMemcpyHostToDevice, s));
-    float* d_comb = nullptr; float* d_met = nullptr; double* d_state = nullptr;
-    double* d_lufs = nullptr; double* d_tp = nullptr;
-    float* d_mag[OMEGA4_MAX_RES] = {nullptr};
-    const size_t rows = (size_t)n_ch * n_hops;
-    if (combined) { rc = p->h_comb.ensure(rows * p->T * sizeof(float)); if (rc) return rc; d_comb = (float*)p->h_comb.p; }
-    if (meters) { rc = p->h_meters.ensure(rows * 5 * sizeof(float)); if (rc) return rc; d_met = (float*)p->h_meters.p; }
-    if (lufs_inst) { rc = p->h_f64a.ensure(rows * sizeof(double)); if (rc) return rc; d_lufs = (double*)p->h_f64a.p; }
-    if (tp_db) { rc = p->h_f64b.ensure(rows * sizeof(double)); if (rc) return rc; d_tp = (double*)p->h_f64b.p; }
-    if (meter_state) {
-        rc = p->h_f64c.ensure((size_t)n_ch * ST_STATE * sizeof(double)); if (rc) return rc;
-        d_state = (double*)p->h_f64c.p;
-        CK(cudaMemcpyAsync(d_state, meter_state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyHostToDevice, s));
+    const long long hist_al = (hist + 3) / 4 * 4;                 // keep device rows 16-byte aligned
+    const long long new_len = (long long)n_hops * p->hop;
+    const long long dstride = (hist_al + new_len + 3) / 4 * 4;
+    size_t per_ch = (size_t)dstride * sizeof(float) + (size_t)n_hops * 2 * sizeof(double) + ST_STATE * sizeof(double);
+    if (combined) per_ch += (size_t)n_hops * p->T * sizeof(float);
+    if (meters) per_ch += (size_t)n_hops * 5 * sizeof(float);
+    bool want_mag[OMEGA4_MAX_RES] = {false};
+    for (int r = 0; r < p->n_res; ++r) {
+        want_mag[r] = (magnitudes && magnitudes[r]) || (combined && !p->disjoint);
+        if (want_mag[r]) per_ch += (size_t)n_hops * p->res[r].bins * sizeof(float);
     }
-    bool any_mag = false;
-    if (magnitudes)
+    int chunk = (int)(p->host_chunk_bytes / per_ch);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_ch) chunk = n_ch;
+    const bool want_series = meters || lufs_inst || tp_db;
+    int idx = 0;
+    for (int c0 = 0; c0 < n_ch; c0 += chunk, ++idx) {
+        const int nc = (n_ch - c0 < chunk) ? n_ch - c0 : chunk;
+        omega4_plan::Slot& sl = p->slots[idx % omega4_plan::N_SLOTS];
+        if (!sl.s) CK(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking));
+        const size_t rows = (size_t)nc * n_hops;
+        int rc = sl.in.ensure((size_t)nc * dstride * sizeof(float)); if (rc) return rc;
+        float* d_in = (float*)sl.in.p;
+        CK(cudaMemcpy2DAsync(d_in + (hist_al - hist), dstride * sizeof(float),
+                             samples + (long long)c0 * ch_stride - hist, ch_stride * sizeof(float),
+                             (size_t)(hist + new_len) * sizeof(float), nc, cudaMemcpyHostToDevice, sl.s));
+        float* d_comb = nullptr; float* d_met = nullptr; double* d_state = nullptr;
+        double* d_lufs = nullptr; double* d_tp = nullptr;
+        float* d_mag[OMEGA4_MAX_RES] = {nullptr};
+        if (combined) { rc = sl.comb.ensure(rows * p->T * sizeof(float)); if (rc) return rc; d_comb = (float*)sl.comb.p; }
+        if (meters) { rc = sl.met.ensure(rows * 5 * sizeof(float)); if (rc) return rc; d_met = (float*)sl.met.p; }
+        if (want_series) {
+            rc = sl.lufs.ensure(rows * sizeof(double)); if (rc) return rc; d_lufs = (double*)sl.lufs.p;
+            rc = sl.tp.ensure(rows * sizeof(double)); if (rc) return rc; d_tp = (double*)sl.tp.p;
+        }
+        if (meters) {
+            rc = sl.state.ensure((size_t)nc * ST_STATE * sizeof(double)); if (rc) return rc;
+            d_state = (double*)sl.state.p;
+            if (meter_state && !(flags & OMEGA4_FLAG_FRESH_METERS))
+                CK(cudaMemcpyAsync(d_state, meter_state + (size_t)c0 * ST_STATE, (size_t)nc * ST_STATE * sizeof(double),
+                                   cudaMemcpyHostToDevice, sl.s));
+        }
+        bool any_mag = false;
         for (int r = 0; r < p->n_res; ++r)
-            if (magnitudes[r]) {
-                rc = p->h_mag[r].ensure(rows * p->res[r].bins * sizeof(float)); if (rc) return rc;
-                d_mag[r] = (float*)p->h_mag[r].p; any_mag = true;
+            if (want_mag[r]) {
+                rc = sl.mag[r].ensure(rows * p->res[r].bins * sizeof(float)); if (rc) return rc;
+                d_mag[r] = (float*)sl.mag[r].p; any_mag = true;
             }
-    rc = analyze_device(p, s, d_in + hist_al, dstride, n_ch, n_hops, (int)hist,
-                        d_comb, any_mag ? d_mag : nullptr, d_met, d_lufs, d_tp, d_state, flags);
-    if (rc) return rc;
-    if (combined) CK(cudaMemcpyAsync(combined, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (meters) CK(cudaMemcpyAsync(meters, d_met, rows * 5 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (lufs_inst) CK(cudaMemcpyAsync(lufs_inst, d_lufs, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (tp_db) CK(cudaMemcpyAsync(tp_db, d_tp, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (meter_state) CK(cudaMemcpyAsync(meter_state, d_state, (size_t)n_ch * ST_STATE * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (magnitudes)
-        for (int r = 0; r < p->n_res; ++r)
-            if (magnitudes[r]) CK(cudaMemcpyAsync(magnitudes[r], d_mag[r], rows * p->res[r].bins * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+        const int fl = flags | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
+        rc = analyze_device(p, sl.s, d_in + hist_al, dstride, nc, n_hops, (int)hist, d_comb, any_mag ? d_mag : nullptr,
+                            d_met, d_lufs, d_tp, d_state, fl);
+        if (rc) return rc;
+        const size_t r0 = (size_t)c0 * n_hops;
+        if (combined) CK(cudaMemcpyAsync(combined + r0 * p->T, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
+        if (meters) CK(cudaMemcpyAsync(meters + r0 * 5, d_met, rows * 5 * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
+        if (lufs_inst) CK(cudaMemcpyAsync(lufs_inst + r0, d_lufs, rows * sizeof(double), cudaMemcpyDeviceToHost, sl.s));
+        if (tp_db) CK(cudaMemcpyAsync(tp_db + r0, d_tp, rows * sizeof(double), cudaMemcpyDeviceToHost, sl.s));
+        if (meters && meter_state)
+            CK(cudaMemcpyAsync(meter_state + (size_t)c0 * ST_STATE, d_state, (size_t)nc * ST_STATE * sizeof(double),
+                               cudaMemcpyDeviceToHost, sl.s));
+        if (magnitudes)
+            for (int r = 0; r < p->n_res; ++r)
+                if (magnitudes[r])
+                    CK(cudaMemcpyAsync(magnitudes[r] + r0 * p->res[r].bins, d_mag[r], rows * p->res[r].bins * sizeof(float),
+                                       cudaMemcpyDeviceToHost, sl.s));
+    }
+    for (auto& sl : p->slots)
+        if (sl.s) CK(cudaStreamSynchronize(sl.s));
     return OMEGA4_OK;
 }
 

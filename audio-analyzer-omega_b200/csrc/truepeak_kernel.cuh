@@ -40,6 +40,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
     constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
     constexpr int RSTRIDE = TPF + TPF / 16;
     constexpr int WARPS_PER_FFT = (TPF + 31) / 32;
+    static_assert(TPF >= 32 && S::PINGPONG, "true-peak kernel needs whole warps per sub-FFT and two buffers");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufs = reinterpret_cast<float2*>(smem_raw);
     float2* xs_all = bufs + (size_t)CONC * 2 * BUF;                // [CONC][M+1] spectrum

@@ -271,3 +271,19 @@ def test_meters_long_statistics(golden):
     np.testing.assert_allclose(rows, g["meters"], rtol=0, atol=1e-9)
     assert len(st.integ) == 3600                                   # the 60 s deque saturated
     assert (g["lufs_inst"] <= -70).sum() > 100                     # gate exercised
+
+
+def test_ref_port_matches_oracle(golden):
+    """The per-hop scipy-based port that bench.py times as the CPU baseline is the same function
+    as the batched oracle (and therefore as the reference goldens)."""
+    pytest.importorskip("scipy.signal")
+    from oracle import ref_port
+    g = golden("meters_stream.npz")
+    x = g["x"][:60 * HOP]
+    comb, meters = ref_port.run_channel(x)
+    ref = O.analyze_channel(x, 48000, O.BASELINE_CONFIGS)
+    np.testing.assert_allclose(comb, ref["combined"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(meters, ref["meters"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(meters[3:], g["meters"][:57], rtol=0, atol=1e-8)
+    r = ref_port.time_cpu_path(2, 2, 0.25, processes=2)
+    assert r["value"] > 0 and r["cores"] == 2
