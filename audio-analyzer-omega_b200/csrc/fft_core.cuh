@@ -241,6 +241,93 @@ __device__ __forceinline__ float2* fft_forward(float2* v, float2* buf0, float2* 
     return src;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Local" variant for M <= 4096 (LOG2M 8..12): only ONE all-to-all exchange.
+// After the first radix-16 DIF stage the transform splits into 16 independent sub-FFTs of
+// n2 = M/16 points (output index = q mod 16).  Sub-FFT q is owned by G2 = M/256 CONSECUTIVE
+// threads (<= 16, inside one warp), so its radix-16 stage, the 16 x G2 exchange and the final
+// radix-G2 stage need only __syncwarp().  CTA barriers per transform: 2 (after the stage-1 store,
+// after the final store) instead of 4 -- ncu showed 21 % of the stall samples at barriers.
+//   X buffer (BUF float2, "grouped"): sub-FFT q lives at X[q*S .. q*S+n2), S = 17*G2; the same
+//       region is reused for the exchange with slot(p,k) = 17p + k.  All accesses conflict free.
+//   Z buffer (M float2, natural order, XOR swizzle zaddr()): conflict free for the final store
+//       (lanes vary in q and p) and for consecutive reads by the epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int LOG2M>
+__host__ __device__ __forceinline__ constexpr int zaddr(int idx) {
+    constexpr int G2 = (1 << LOG2M) / 256;
+    return (idx & ~15) | ((idx & 15) ^ ((((idx >> 4) & (G2 - 1)) * (16 / G2)) & 15));
+}
+
+template <int LOG2M>
+struct LocalTw { Tw4 s1, s2; };
+
+template <int LOG2M>
+__device__ __forceinline__ void load_local_twiddles(LocalTw<LOG2M>& st, const float2* __restrict__ twM, int t) {
+    constexpr int G2 = (1 << LOG2M) / 256;
+    st.s1.w1 = __ldg(twM + t);     st.s1.w2 = __ldg(twM + 2 * t);
+    st.s1.w4 = __ldg(twM + 4 * t); st.s1.w8 = __ldg(twM + 8 * t);
+    const int e = 16 * (t % G2);
+    st.s2.w1 = __ldg(twM + e);     st.s2.w2 = __ldg(twM + 2 * e);
+    st.s2.w4 = __ldg(twM + 4 * e); st.s2.w8 = __ldg(twM + 8 * e);
+}
+
+// On entry v[16] = z[t + j*M/16].  X, Z: this sub-FFT group's buffers.  Contains two
+// __syncthreads() (after the stage-1 store; after the final store unless KEEP_LAST_IN_REGS).
+// MID is invoked by every thread right after the first barrier (used to overlap deferred work).
+// With KEEP_LAST_IN_REGS the final outputs stay in v[] (butterfly i of the last stage in
+// v[i*G2 .. i*G2+G2)) and nothing is written to Z.
+template <int LOG2M, bool KEEP_LAST_IN_REGS, typename Mid>
+__device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* Z, const LocalTw<LOG2M>& st,
+                                                  int t, bool active, Mid&& mid) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int G2 = M / 256;
+    constexpr int S = 17 * G2;
+    static_assert(LOG2M >= 8 && LOG2M <= 12, "local variant covers 256 .. 4096 complex points");
+    if (active) {
+        bf16pt(v);
+        apply_twiddles(v, st.s1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) X[k * S + t] = v[k];
+    }
+    __syncthreads();
+    mid();
+    if (active) {
+        const int q = t / G2, p = t % G2;
+        float2* Xq = X + q * S;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = Xq[p + G2 * j];
+        bf16pt(v);
+        if (G2 == 1) {
+            if (!KEEP_LAST_IN_REGS) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) Z[zaddr<LOG2M>(q + 16 * k)] = v[k];
+            }
+        } else {
+            apply_twiddles(v, st.s2);
+            __syncwarp();                         // every lane of the group holds its inputs in registers
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Xq[17 * p + k] = v[k];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16 / G2; ++i) {
+                const int k = p + G2 * i;
+#pragma unroll
+                for (int pp = 0; pp < G2; ++pp) v[i * G2 + pp] = Xq[17 * pp + k];
+                if (G2 == 2) bf2(v[i * 2], v[i * 2 + 1]);
+                if (G2 == 4) bf4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+                if (G2 == 8) bf8(v + i * 8);
+                if (G2 == 16) bf16pt(v);
+                if (!KEEP_LAST_IN_REGS) {
+#pragma unroll
+                    for (int pq = 0; pq < G2; ++pq) Z[zaddr<LOG2M>(q + 16 * k + 256 * pq)] = v[i * G2 + pq];
+                }
+            }
+        }
+    }
+    if (!KEEP_LAST_IN_REGS) __syncthreads();
+}
+
 // Untangle one (k, M-k) pair of the packed real transform.
 //   Zk = Z[k], Zm = Z[(M-k) % M], w = W_N^k = exp(-2 pi i k / N), N = 2M
 //   X[k] = E + w*O,  X[M-k] = conj(E - w*O),  E = (Zk + conj Zm)/2,  O = -i (Zk - conj Zm)/2

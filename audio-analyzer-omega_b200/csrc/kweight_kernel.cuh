@@ -11,15 +11,18 @@
 // Mapping: ONE WARP PER FRAME, block-parallel linear-recurrence scan.  The padded frame has
 // W + 18 = 2066 samples; lane l owns the 65 consecutive samples [65 l, 65 l + 65) in REGISTERS
 // (fp64) for all four IIR passes.  Each pass:
-//   1. every lane runs the biquad (transposed direct form II, as scipy's lfilter) over its chunk
-//      from zero state  -> zero-state outputs + end state e_l
-//   2. the true chunk-entry states follow v_l = Phi v_{l-1} + e_l (Phi = A^65) -> 5-step
-//      Kogge-Stone scan with shuffles, multipliers Phi^(2^j) precomputed on the host
+//   1. every lane runs the biquad over its chunk from zero OUTPUT state (the two previous inputs
+//      come from the neighbouring lane) -> zero-state outputs + end state e_l = (y[64], y[63]).
+//      The recursion is written in direct form I, y[n] = (u[n] - a2 y[n-2]) - a1 y[n-1], so that
+//      only ONE fp64 FMA per sample sits on the dependency chain (scipy's transposed form II has
+//      two; ncu showed the kernel bound by exactly that fixed-latency chain).  scipy's initial
+//      state zi*x0 is converted once into the equivalent (y[-1], y[-2]).
+//   2. the true chunk-entry states follow v_l = Phi v_{l-1} + e_l (Phi = C^65, C the companion
+//      matrix) -> 5-step Kogge-Stone scan with shuffles, multipliers Phi^(2^j) from the host
 //   3. every lane adds the homogeneous response g[i] . s_in to its outputs
 // Backward passes run the same code with lane order and sample order reversed.  The 14 slack
-// positions of lane 31 are zeroed before a backward pass and the steady-state start
-// zi * y[last] is moved 14 steps back in time (s_virt = A^-14 zi y_last) so that all lanes stay
-// uniform.  fp64 state is required: the 38 Hz poles sit at radius 0.9965 and fp32 coefficients
+// positions of lane 31 are zeroed before a backward pass and the steady-state start is moved 14
+// steps back in time (s_virt = C^-14 s_init) so that all lanes stay uniform.  fp64 state is required: the 38 Hz poles sit at radius 0.9965 and fp32 coefficients
 // alone would move the cut-off by ~0.2 % ("IIR precision").
 #pragma once
 #include <cuda_runtime.h>
@@ -32,13 +35,19 @@ constexpr int KW_L = 65;            // samples per lane
 constexpr int KW_EXT = KW_W + 2 * KW_PAD;       // 2066
 constexpr int KW_SLACK = 32 * KW_L - KW_EXT;    // 14
 constexpr int KW_LAST = KW_L - 1 - KW_SLACK;    // 50: local index of ext[2065] on lane 31
+// every lane's 65 samples are swept as 4 independent sub-chunks of 17+16+16+16 samples: four
+// interleaved dependency chains hide the fp64 FMA latency that a single chain exposes
+constexpr int KW_NSUB = 4;
+constexpr int KW_SUBMAX = 17;
+__host__ __device__ constexpr int kw_off(int j) { return j == 0 ? 0 : 17 + 16 * (j - 1); }   // 0,17,33,49,65
 
 struct KwBiquad {
     double b0, b1, b2, a1, a2;
-    double zi0, zi1;                // lfilter_zi
-    double phi[5][4];               // (A^65)^(2^j), row major [[p00,p01],[p10,p11]]
-    double ainv[4];                 // A^-14
-    double g[KW_L][2];              // g[i] = first row of A^i  (homogeneous output response)
+    double yi0, yi1;                // (y[-1], y[-2]) per unit x0, equivalent to scipy's lfilter_zi state
+    double phi[5][4];               // (C^65)^(2^j), row major [[p00,p01],[p10,p11]], C = [[-a1,-a2],[1,0]]
+    double cinv[4];                 // C^-14
+    double c16[4], c17[4];          // C^16, C^17: transitions over one sub-chunk
+    double g[KW_SUBMAX][2];         // g[i] = first row of C^(i+1)  (homogeneous output response)
 };
 
 struct KweightArgs {
@@ -72,44 +81,91 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
 #pragma unroll
         for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = 0.0;
     }
-    double2 s_init = make_double2(c.zi0 * x0, c.zi1 * x0);
-    if (BACKWARD) s_init = mat2_apply(c.ainv, s_init);
+    double2 s_init = make_double2(c.yi0 * x0, c.yi1 * x0);
+    if (BACKWARD) s_init = mat2_apply(c.cinv, s_init);
 
-    // 1. zero-state sweep
-    double z1 = 0.0, z2 = 0.0;
+    // sub-chunk m (processing order) = index range j: forward j = m, backward j = 3 - m
+    // length of sub-chunk m in processing order: forward 17,16,16,16 ; backward 16,16,16,17
+    double xa[KW_NSUB], xb[KW_NSUB];      // the two inputs preceding each sub-chunk (processing order)
+    xa[0] = BACKWARD ? __shfl_down_sync(0xffffffffu, r[0], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 1], 1);
+    xb[0] = BACKWARD ? __shfl_down_sync(0xffffffffu, r[1], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 2], 1);
+    if (pos == 0) { xa[0] = 0.0; xb[0] = 0.0; }
 #pragma unroll
-    for (int n = 0; n < KW_L; ++n) {
-        const int i = BACKWARD ? KW_L - 1 - n : n;
-        double x = r[i];
-        double y = fma(c.b0, x, z1);
-        z1 = fma(-c.a1, y, fma(c.b1, x, z2));
-        z2 = fma(-c.a2, y, c.b2 * x);
-        r[i] = y;
+    for (int m = 1; m < KW_NSUB; ++m) {
+        const int j = BACKWARD ? KW_NSUB - 1 - m : m;
+        xa[m] = BACKWARD ? r[kw_off(j + 1)] : r[kw_off(j) - 1];
+        xb[m] = BACKWARD ? r[kw_off(j + 1) + 1] : r[kw_off(j) - 2];
     }
-    // 2. scan of chunk end states
-    double2 v = make_double2(z1, z2);
+    // 1. zero-state sweeps, direct form I, four independent chains
+    double y1[KW_NSUB], y2[KW_NSUB];
+#pragma unroll
+    for (int m = 0; m < KW_NSUB; ++m) { y1[m] = 0.0; y2[m] = 0.0; }
+#pragma unroll
+    for (int n = 0; n < KW_SUBMAX; ++n) {
+#pragma unroll
+        for (int m = 0; m < KW_NSUB; ++m) {
+            const int j = BACKWARD ? KW_NSUB - 1 - m : m;
+            const int len = kw_off(j + 1) - kw_off(j);
+            if (n < len) {
+                const int i = BACKWARD ? kw_off(j + 1) - 1 - n : kw_off(j) + n;
+                const double x = r[i];
+                const double u = fma(c.b0, x, fma(c.b1, xa[m], c.b2 * xb[m]));
+                const double t = fma(-c.a2, y2[m], u);
+                const double y = fma(-c.a1, y1[m], t);
+                xb[m] = xa[m]; xa[m] = x;
+                y2[m] = y1[m]; y1[m] = y;
+                r[i] = y;
+            }
+        }
+    }
+    // lane aggregate: zero-state end state of the whole 65-sample chunk
+    double2 v = make_double2(y1[0], y2[0]);
+#pragma unroll
+    for (int m = 1; m < KW_NSUB; ++m) {
+        const int j = BACKWARD ? KW_NSUB - 1 - m : m;
+        const double* cm = (kw_off(j + 1) - kw_off(j) == 17) ? c.c17 : c.c16;
+        double2 q = mat2_apply(cm, v);
+        v = make_double2(q.x + y1[m], q.y + y2[m]);
+    }
+    // 2. scan of chunk end states across lanes
     if (pos == 0) {
         double2 q = mat2_apply(c.phi[0], s_init);
         v.x += q.x; v.y += q.y;
     }
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int d = 1 << j;
+    for (int jj = 0; jj < 5; ++jj) {
+        const int d = 1 << jj;
         double rx = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, d) : __shfl_up_sync(0xffffffffu, v.x, d);
         double ry = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, d) : __shfl_up_sync(0xffffffffu, v.y, d);
         if (pos >= d) {
-            double2 q = mat2_apply(c.phi[j], make_double2(rx, ry));
+            double2 q = mat2_apply(c.phi[jj], make_double2(rx, ry));
             v.x += q.x; v.y += q.y;
         }
     }
-    double sx = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, 1) : __shfl_up_sync(0xffffffffu, v.x, 1);
-    double sy = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, 1) : __shfl_up_sync(0xffffffffu, v.y, 1);
-    if (pos == 0) { sx = s_init.x; sy = s_init.y; }
+    double2 sin[KW_NSUB];
+    sin[0].x = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, 1) : __shfl_up_sync(0xffffffffu, v.x, 1);
+    sin[0].y = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, 1) : __shfl_up_sync(0xffffffffu, v.y, 1);
+    if (pos == 0) sin[0] = s_init;
+    // entry state of every sub-chunk: s_m = C^len(m-1) s_(m-1) + e_(m-1)
+#pragma unroll
+    for (int m = 1; m < KW_NSUB; ++m) {
+        const int jp = BACKWARD ? KW_NSUB - m : m - 1;              // index range of sub-chunk m-1
+        const double* cm = (kw_off(jp + 1) - kw_off(jp) == 17) ? c.c17 : c.c16;
+        double2 q = mat2_apply(cm, sin[m - 1]);
+        sin[m] = make_double2(q.x + y1[m - 1], q.y + y2[m - 1]);
+    }
     // 3. homogeneous correction
 #pragma unroll
-    for (int n = 0; n < KW_L; ++n) {
-        const int i = BACKWARD ? KW_L - 1 - n : n;
-        r[i] = fma(c.g[n][0], sx, fma(c.g[n][1], sy, r[i]));
+    for (int n = 0; n < KW_SUBMAX; ++n) {
+#pragma unroll
+        for (int m = 0; m < KW_NSUB; ++m) {
+            const int j = BACKWARD ? KW_NSUB - 1 - m : m;
+            const int len = kw_off(j + 1) - kw_off(j);
+            if (n < len) {
+                const int i = BACKWARD ? kw_off(j + 1) - 1 - n : kw_off(j) + n;
+                r[i] = fma(c.g[n][0], sin[m].x, fma(c.g[n][1], sin[m].y, r[i]));
+            }
+        }
     }
 }
 
@@ -128,18 +184,40 @@ __device__ __forceinline__ void kw_odd_pad(double (&r)[KW_L], int lane) {
 }
 
 constexpr int KW_WARPS = 4;
+#ifndef KW_MIN_BLOCKS
+#define KW_MIN_BLOCKS 2
+#endif
+// per-warp staging strip in "ext" coordinates shifted by 3 floats so that the frame's first sample
+// (ext position 9) lands on a 16-byte boundary: index = ext position + 3
+constexpr int KW_STG_SHIFT = 3;
+constexpr int KW_STG = 32 * KW_L + 16;          // 2096 floats per warp
 
-__global__ void __launch_bounds__(KW_WARPS * 32, 2)
+__device__ __forceinline__ void kw_zero_pads(double (&r)[KW_L], int lane) {
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < KW_PAD; ++i) r[i] = 0.0;
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int i = KW_LAST - KW_PAD + 1; i < KW_L; ++i) r[i] = 0.0;
+    }
+}
+
+// F64_FRAMES: input is explicit float64 frames (streaming shim), else float32 samples + Hann table.
+// WEIGHTED: also store the K-weighted frame (ProfessionalMetering.apply_k_weighting).
+template <bool F64_FRAMES, bool WEIGHTED>
+__global__ void __launch_bounds__(KW_WARPS * 32, KW_MIN_BLOCKS)
 kweight_kernel(const __grid_constant__ KweightArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* hann_s = reinterpret_cast<double*>(smem_raw);                          // [W]
-    float* stage_all = reinterpret_cast<float*>(hann_s + KW_W);                     // [KW_WARPS][32*65]
+    double* hann_x = reinterpret_cast<double*>(smem_raw);                          // [32*65] ext layout, 0 at pads
+    float* stage_all = reinterpret_cast<float*>(hann_x + 32 * KW_L);               // [KW_WARPS][KW_STG]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float* stg = stage_all + warp * (32 * KW_L);
+    float* stg = stage_all + warp * KW_STG;
 
-    if (a.hann) {
-        for (int i = threadIdx.x; i < KW_W; i += blockDim.x) hann_s[i] = a.hann[i];
+    for (int p = threadIdx.x; p < 32 * KW_L; p += blockDim.x) {
+        const int n = p - KW_PAD;
+        hann_x[p] = (n >= 0 && n < KW_W) ? (a.hann ? a.hann[n] : 1.0) : 0.0;
     }
     __syncthreads();
 
@@ -155,22 +233,25 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
 
         double r[KW_L];
         double sumsq = 0.0;
-        if (!a.x_is_f64) {
-            // coalesced copy of the frame into shared memory, then strided (conflict free) reads
+        if (!F64_FRAMES) {
+            // coalesced copy of the frame into the staging strip (pads zeroed), then conflict-free
+            // strided reads: no per-element predicates anywhere
             const float4* px = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + off);
-            float4* s4 = reinterpret_cast<float4*>(stg);
+            float4* s4 = reinterpret_cast<float4*>(stg + KW_PAD + KW_STG_SHIFT);
+            float4 tmp[KW_W / 4 / 32];
 #pragma unroll
-            for (int j = 0; j < KW_W / 4 / 32; ++j) s4[lane + 32 * j] = __ldg(px + lane + 32 * j);
+            for (int j = 0; j < KW_W / 4 / 32; ++j) tmp[j] = __ldg(px + lane + 32 * j);
+            if (lane < KW_PAD) stg[KW_STG_SHIFT + lane] = 0.f;
+            if (lane < KW_SLACK + KW_PAD + KW_STG_SHIFT) stg[KW_STG_SHIFT + KW_PAD + KW_W + lane] = 0.f;
+#pragma unroll
+            for (int j = 0; j < KW_W / 4 / 32; ++j) s4[lane + 32 * j] = tmp[j];
             __syncwarp();
+            const float* sl = stg + KW_STG_SHIFT + KW_L * lane;
+            const double* hl = hann_x + KW_L * lane;
 #pragma unroll
             for (int i = 0; i < KW_L; ++i) {
-                int n = KW_L * lane + i - KW_PAD;                      // frame sample index
-                double xv = 0.0;
-                if (n >= 0 && n < KW_W) {
-                    xv = (double)stg[n];
-                    if (a.hann) xv *= hann_s[n];
-                    sumsq = fma(xv, xv, sumsq);
-                }
+                const double xv = (double)sl[i] * hl[i];
+                sumsq = fma(xv, xv, sumsq);
                 r[i] = xv;
             }
             __syncwarp();
@@ -178,13 +259,10 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
             const double* px = reinterpret_cast<const double*>(a.x) + off;
 #pragma unroll
             for (int i = 0; i < KW_L; ++i) {
-                int n = KW_L * lane + i - KW_PAD;
+                const int n = KW_L * lane + i - KW_PAD;
                 double xv = 0.0;
-                if (n >= 0 && n < KW_W) {
-                    xv = px[n];
-                    if (a.hann) xv *= hann_s[n];
-                    sumsq = fma(xv, xv, sumsq);
-                }
+                if (n >= 0 && n < KW_W) xv = px[n] * hann_x[KW_L * lane + i];
+                sumsq = fma(xv, xv, sumsq);
                 r[i] = xv;
             }
         }
@@ -194,32 +272,40 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
 
         double ms = 0.0;
         if (!gated) {                                                  // warp-uniform
+            float* fl = stg + KW_STG_SHIFT + KW_L * lane;
             kw_odd_pad(r, lane);
             kw_pass<false>(r, a.f[0], lane);
             kw_pass<true>(r, a.f[0], lane);
-            // stash f (first filtfilt output) as fp32; 65-word lane stride is bank-conflict free
+            // stash f (first filtfilt output) as fp32 with zeros at the pad positions;
+            // the 65-word lane stride is bank-conflict free
+            kw_zero_pads(r, lane);
 #pragma unroll
-            for (int i = 0; i < KW_L; ++i) stg[KW_L * lane + i] = (float)r[i];
+            for (int i = 0; i < KW_L; ++i) fl[i] = (float)r[i];
             kw_odd_pad(r, lane);
             kw_pass<false>(r, a.f[1], lane);
             kw_pass<true>(r, a.f[1], lane);
+            kw_zero_pads(r, lane);
             double acc = 0.0;
-            double* wrow = a.weighted_out ? a.weighted_out + ((size_t)ch * a.n_frames + f) * KW_W : nullptr;
 #pragma unroll
             for (int i = 0; i < KW_L; ++i) {
-                int n = KW_L * lane + i - KW_PAD;
-                if (n >= 0 && n < KW_W) {
-                    double fv = (double)stg[KW_L * lane + i];
-                    double w = fma(r[i] - fv, 0.3, fv);                // f + (s - f) * 0.3
-                    acc = fma(w, w, acc);
-                    if (wrow) wrow[n] = w;
-                }
+                const double fv = (double)fl[i];
+                const double w = fma(r[i] - fv, 0.3, fv);              // f + (s - f) * 0.3 ; 0 at the pads
+                acc = fma(w, w, acc);
+                if (WEIGHTED) r[i] = w;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             ms = acc / (double)KW_W;
+            if (WEIGHTED && a.weighted_out) {
+                double* wrow = a.weighted_out + ((size_t)ch * a.n_frames + f) * KW_W;
+#pragma unroll
+                for (int i = 0; i < KW_L; ++i) {
+                    const int n = KW_L * lane + i - KW_PAD;
+                    if (n >= 0 && n < KW_W) wrow[n] = r[i];
+                }
+            }
             __syncwarp();
-        } else if (a.weighted_out) {
+        } else if (WEIGHTED && a.weighted_out) {
             double* wrow = a.weighted_out + ((size_t)ch * a.n_frames + f) * KW_W;
             for (int n = lane; n < KW_W; n += 32) wrow[n] = 0.0;
         }
@@ -229,7 +315,7 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
 }
 
 inline size_t kweight_smem_bytes() {
-    return (size_t)KW_W * sizeof(double) + (size_t)KW_WARPS * 32 * KW_L * sizeof(float);
+    return (size_t)32 * KW_L * sizeof(double) + (size_t)KW_WARPS * KW_STG * sizeof(float);
 }
 
 }  // namespace o4

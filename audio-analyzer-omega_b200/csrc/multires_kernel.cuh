@@ -7,6 +7,10 @@
 //   MultiResolutionFFT.combine_results_optimized       (:359-395, tables precomputed on host)
 //   BatchedFFTProcessor._process_size_group_cpu/gpu     (omega4/optimization/batched_fft_processor.py:197-285)
 //   GPUAcceleratedFFT.compute_fft / process_fft_batch   (omega4/optimization/gpu_accelerated_fft.py:92-177,300-340)
+//
+// Two kernels share the epilogue:
+//   multires_local_kernel<LOG2M>  N = 512 .. 8192   (fft_forward_local: 2 CTA barriers per round)
+//   multires_kernel<LOG2M>        N = 16384, 32768  (generic multi-stage Stockham)
 #pragma once
 #include "fft_core.cuh"
 
@@ -37,21 +41,86 @@ struct MultiresArgs {
     int need_lo, need_cnt;     // FFT bins [need_lo, need_lo + need_cnt) feed the combine step
 };
 
+struct ZPadded { __device__ static __forceinline__ int at(int i) { return padi(i); } };
 template <int LOG2M>
-__global__ void __launch_bounds__(FftShape<LOG2M>::NT, (FftShape<LOG2M>::NT <= 256 ? 2 : 1))
-multires_kernel(const __grid_constant__ MultiresArgs a) {
+struct ZSwizzled { __device__ static __forceinline__ int at(int i) { return zaddr<LOG2M>(i); } };
+
+// Untangle + |X| * weight for the bins this thread owns: pairs u = t + i*TPF in [0, M/2), plus
+// u = M/2 handled by thread 0.  In fused mode (no mag/complex output) only the bins the combine
+// step needs are evaluated.
+template <int LOG2M, typename ZA>
+__device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const float2* Z, float* mags, int t,
+                                                  size_t row, bool active) {
+    using S = FftShape<LOG2M>;
+    constexpr int M = S::M, TPF = S::TPF;
+    const bool all_bins = (a.mag_out != nullptr) || (a.cplx_out != nullptr);
+    const int need_hi = a.need_lo + a.need_cnt;
+    float* mrow = a.mag_out ? a.mag_out + row * (M + 1) : nullptr;
+    float2* crow = a.cplx_out ? a.cplx_out + row * (M + 1) : nullptr;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int u = (i < 8) ? t + i * TPF : M / 2;
+        if (i == 8 && t != 0) break;
+        const int k = u, km = M - u;
+        const bool ink = (k >= a.need_lo && k < need_hi);
+        const bool inm = (km >= a.need_lo && km < need_hi);
+        if (!(all_bins || ink || inm)) continue;
+        float mk = 0.f, mm = 0.f;
+        float2 Xk = make_float2(0.f, 0.f), Xm = Xk;
+        if (active) {
+            const float2 Zk = Z[ZA::at(u)];
+            const float2 Zm = Z[ZA::at((M - u) & (M - 1))];
+            const float2 w = __ldg(a.twN + u);
+            rfft_pair(Zk, Zm, w, Xk, Xm);
+            mk = cabs(Xk);
+            mm = cabs(Xm);
+            if (a.binw) { mk *= __ldg(a.binw + k); mm *= __ldg(a.binw + km); }
+        }
+        if (mrow) { mrow[k] = mk; mrow[km] = mm; }
+        if (crow) { crow[k] = Xk; crow[km] = Xm; }
+        if (ink) mags[k - a.need_lo] = mk;
+        if (inm) mags[km - a.need_lo] = mm;
+    }
+}
+
+// np.interp segments of combine_results_optimized evaluated from the smem strip of magnitudes.
+template <int TPF>
+__device__ __forceinline__ void multires_combine(const MultiresArgs& a, const float* mags, int t, size_t row, bool active) {
+    float* orow = a.comb_out + row * a.T;
+    for (int j = t; j < a.n_tb; j += TPF) {
+        const int lo = __ldg(a.tb_lo + j);
+        float val = 0.f;
+        if (active && lo >= 0) {
+            const float m0 = mags[lo - a.need_lo];
+            const float m1 = mags[lo + 1 - a.need_lo];
+            const float vi = fmaf(m1 - m0, __ldg(a.tb_frac + j), m0);
+            val = (vi * a.wnum) / a.wden;
+        }
+        orow[__ldg(a.tb_idx + j)] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// N = 512 .. 8192
+// ---------------------------------------------------------------------------------------------
+template <int LOG2M>
+__global__ void __launch_bounds__(256, 2)
+multires_local_kernel(const __grid_constant__ MultiresArgs a) {
     using S = FftShape<LOG2M>;
     constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
+    static_assert(S::NT == 256, "local kernel runs 256-thread CTAs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* bufs = reinterpret_cast<float2*>(smem_raw);
-    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * S::NBUF * BUF);
+    float2* bufs = reinterpret_cast<float2*>(smem_raw);                            // [CONC][BUF + M]
+    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * (BUF + M));   // [2][CONC][need_cnt]
 
     const int tid = threadIdx.x;
     const int g = tid / TPF;
     const int t = tid % TPF;
-    float2* buf0 = bufs + (size_t)g * S::NBUF * BUF;
-    float2* buf1 = S::PINGPONG ? buf0 + BUF : buf0;
-    float* mags = mags_all + (size_t)g * a.need_cnt;
+    float2* X = bufs + (size_t)g * (BUF + M);
+    float2* Z = X + BUF;
+    const int mstride = a.need_cnt > 0 ? a.need_cnt : 1;
+    float* mags0 = mags_all + (size_t)g * mstride;
+    float* mags1 = mags0 + (size_t)CONC * mstride;
 
     const int frames_per_cta = a.rounds * CONC;
     const int tiles_per_ch = (a.n_frames + frames_per_cta - 1) / frames_per_cta;
@@ -64,16 +133,102 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
         win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
+    LocalTw<LOG2M> st;
+    load_local_twiddles<LOG2M>(st, a.twM, t);
+
+    const float* xch = a.x + (long long)ch * a.ch_stride + a.frame_off0;
+    float2 v[16];
+    {
+        const int f = f0 + g;
+        if (f < a.n_frames && f >= a.first_frame) {
+            const float2* px = reinterpret_cast<const float2*>(xch + (long long)f * a.frame_stride);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
+        }
+    }
+
+    for (int r = 0; r < a.rounds; ++r) {
+        const int f = f0 + r * CONC + g;
+        const bool valid = f < a.n_frames;
+        const bool active = valid && f >= a.first_frame;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j].x *= win[j].x; v[j].y *= win[j].y; }
+        }
+        // the combine of the previous round runs right after this round's first barrier, which
+        // also publishes the previous epilogue's magnitudes
+        fft_forward_local<LOG2M, false>(v, X, Z, st, t, active, [&]() {
+            if (r > 0 && a.comb_out) {
+                const int fp = f - CONC;
+                if (fp < a.n_frames)
+                    multires_combine<TPF>(a, ((r - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fp,
+                                          fp >= a.first_frame);
+            }
+        });
+        // prefetch the next round's samples; they land while the epilogue runs
+        {
+            const int fn = f + CONC;
+            if (r + 1 < a.rounds && fn < a.n_frames && fn >= a.first_frame) {
+                const float2* px = reinterpret_cast<const float2*>(xch + (long long)fn * a.frame_stride);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
+            }
+        }
+        if (valid)
+            multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active);
+    }
+    if (a.comb_out) {
+        __syncthreads();
+        const int fl = f0 + (a.rounds - 1) * CONC + g;
+        if (fl < a.n_frames)
+            multires_combine<TPF>(a, ((a.rounds - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fl,
+                                  fl >= a.first_frame);
+    }
+}
+
+template <int LOG2M>
+inline size_t multires_local_smem_bytes(int need_cnt) {
+    using S = FftShape<LOG2M>;
+    return (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) +
+           (size_t)2 * S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float);
+}
+
+// ---------------------------------------------------------------------------------------------
+// N = 16384, 32768 (generic multi-stage path)
+// ---------------------------------------------------------------------------------------------
+template <int LOG2M>
+__global__ void __launch_bounds__(FftShape<LOG2M>::NT, (FftShape<LOG2M>::NT <= 256 ? 2 : 1))
+multires_kernel(const __grid_constant__ MultiresArgs a) {
+    using S = FftShape<LOG2M>;
+    constexpr int TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufs = reinterpret_cast<float2*>(smem_raw);
+    float* mags_all = reinterpret_cast<float*>(bufs + (size_t)CONC * S::NBUF * BUF);
+
+    const int tid = threadIdx.x;
+    const int g = tid / TPF;
+    const int t = tid % TPF;
+    float2* buf0 = bufs + (size_t)g * S::NBUF * BUF;
+    float2* buf1 = S::PINGPONG ? buf0 + BUF : buf0;
+    float* mags = mags_all + (size_t)g * (a.need_cnt > 0 ? a.need_cnt : 1);
+
+    const int frames_per_cta = a.rounds * CONC;
+    const int tiles_per_ch = (a.n_frames + frames_per_cta - 1) / frames_per_cta;
+    const int ch = blockIdx.x / tiles_per_ch;
+    const int tile = blockIdx.x % tiles_per_ch;
+    const int f0 = tile * frames_per_cta;
+
+    float2 win[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
     StageTw<LOG2M> st;
     load_stage_twiddles<LOG2M>(st, a.twM, t);
 
     const float* xch = a.x + (long long)ch * a.ch_stride + a.frame_off0;
-    const bool all_bins = (a.mag_out != nullptr) || (a.cplx_out != nullptr);
-    const int need_hi = a.need_lo + a.need_cnt;   // exclusive
-
     float2 v[16];
     {
-        int f = f0 + g;
+        const int f = f0 + g;
         if (f < a.n_frames && f >= a.first_frame) {
             const float2* px = reinterpret_cast<const float2*>(xch + (long long)f * a.frame_stride);
 #pragma unroll
@@ -90,62 +245,18 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
             for (int j = 0; j < 16; ++j) { v[j].x *= win[j].x; v[j].y *= win[j].y; }
         }
         const float2* Z = fft_forward<LOG2M, false>(v, buf0, buf1, st, t, active);
-
-        // prefetch the next round's samples; they land while the epilogue runs
         {
-            int fn = f + CONC;
+            const int fn = f + CONC;
             if (r + 1 < a.rounds && fn < a.n_frames && fn >= a.first_frame) {
                 const float2* px = reinterpret_cast<const float2*>(xch + (long long)fn * a.frame_stride);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
             }
         }
-
         const size_t row = (size_t)ch * a.n_frames + (valid ? f : 0);
-        if (valid) {
-            float* mrow = a.mag_out ? a.mag_out + row * (M + 1) : nullptr;
-            float2* crow = a.cplx_out ? a.cplx_out + row * (M + 1) : nullptr;
-            // pairs u = t + i*TPF in [0, M/2), plus u = M/2 handled by thread 0 as a 9th pair
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                int u = (i < 8) ? t + i * TPF : M / 2;
-                if (i == 8 && t != 0) break;
-                int k = u, km = M - u;
-                bool nk = all_bins || (k >= a.need_lo && k < need_hi);
-                bool nm = all_bins || (km >= a.need_lo && km < need_hi);
-                if (!(nk || nm)) continue;
-                float mk = 0.f, mm = 0.f;
-                float2 Xk = make_float2(0.f, 0.f), Xm = Xk;
-                if (active) {
-                    float2 Zk = Z[padi(u)];
-                    float2 Zm = Z[padi((M - u) & (M - 1))];
-                    float2 w = __ldg(a.twN + u);
-                    rfft_pair(Zk, Zm, w, Xk, Xm);
-                    mk = cabs(Xk);
-                    mm = cabs(Xm);
-                    if (a.binw) { mk *= __ldg(a.binw + k); mm *= __ldg(a.binw + km); }
-                }
-                if (mrow) { mrow[k] = mk; mrow[km] = mm; }
-                if (crow) { crow[k] = Xk; crow[km] = Xm; }
-                if (k >= a.need_lo && k < need_hi) mags[k - a.need_lo] = mk;
-                if (km >= a.need_lo && km < need_hi) mags[km - a.need_lo] = mm;
-            }
-        }
+        if (valid) multires_epilogue<LOG2M, ZPadded>(a, Z, mags, t, row, active);
         __syncthreads();
-        if (valid && a.comb_out) {
-            float* orow = a.comb_out + row * a.T;
-            for (int j = t; j < a.n_tb; j += TPF) {
-                int lo = __ldg(a.tb_lo + j);
-                float val = 0.f;
-                if (active && lo >= 0) {
-                    float m0 = mags[lo - a.need_lo];
-                    float m1 = mags[lo + 1 - a.need_lo];
-                    float vi = fmaf(m1 - m0, __ldg(a.tb_frac + j), m0);
-                    val = (vi * a.wnum) / a.wden;
-                }
-                orow[__ldg(a.tb_idx + j)] = val;
-            }
-        }
+        if (valid && a.comb_out) multires_combine<TPF>(a, mags, t, row, active);
         // No second barrier needed: every thread has finished reading Z before the barrier above,
         // and the next epilogue's writes to mags are separated from this combine's reads by the
         // barriers inside fft_forward.

@@ -88,14 +88,20 @@ static int get_twiddles(int device, int log2m, Twiddles* out) {
 template <int L>
 static int launch_multires_t(const MultiresArgs& a, cudaStream_t s) {
     using S = FftShape<L>;
-    const size_t smem = multires_smem_bytes<L>(a.need_cnt);
-    CK(cudaFuncSetAttribute(multires_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int fpc = a.rounds * S::CONC;
     const long long tiles = (a.n_frames + fpc - 1) / fpc;
     const long long grid = tiles * a.n_ch;
     if (grid <= 0) return OMEGA4_OK;
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "multires grid too large");
-    multires_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
+    if constexpr (L <= 12) {
+        const size_t smem = multires_local_smem_bytes<L>(a.need_cnt);
+        CK(cudaFuncSetAttribute(multires_local_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        multires_local_kernel<L><<<(unsigned)grid, 256, smem, s>>>(a);
+    } else {
+        const size_t smem = multires_smem_bytes<L>(a.need_cnt);
+        CK(cudaFuncSetAttribute(multires_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        multires_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
     return OMEGA4_OK;
 }
@@ -134,16 +140,22 @@ static int launch_truepeak(const TruePeakArgs& a, cudaStream_t s) {
     return OMEGA4_OK;
 }
 
-static int launch_kweight(const KweightArgs& a, cudaStream_t s) {
+template <bool F64, bool WT>
+static int launch_kweight_t(const KweightArgs& a, cudaStream_t s) {
     const size_t smem = kweight_smem_bytes();
-    CK(cudaFuncSetAttribute(kweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kweight_kernel<F64, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int fpc = a.frames_per_warp * KW_WARPS;
     const long long grid = (long long)((a.n_frames + fpc - 1) / fpc) * a.n_ch;
     if (grid <= 0) return OMEGA4_OK;
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "kweight grid too large");
-    kweight_kernel<<<(unsigned)grid, KW_WARPS * 32, smem, s>>>(a);
+    kweight_kernel<F64, WT><<<(unsigned)grid, KW_WARPS * 32, smem, s>>>(a);
     CK(cudaGetLastError());
     return OMEGA4_OK;
+}
+
+static int launch_kweight(const KweightArgs& a, cudaStream_t s) {
+    if (a.x_is_f64) return a.weighted_out ? launch_kweight_t<true, true>(a, s) : launch_kweight_t<true, false>(a, s);
+    return a.weighted_out ? launch_kweight_t<false, true>(a, s) : launch_kweight_t<false, false>(a, s);
 }
 
 static int launch_stats(const StatsArgs& a, cudaStream_t s) {
@@ -169,28 +181,34 @@ static void build_biquad(const double* b, const double* a, KwBiquad* q) {
     q->b0 = b[0] / a0; q->b1 = b[1] / a0; q->b2 = b[2] / a0;
     q->a1 = a[1] / a0; q->a2 = a[2] / a0;
     // lfilter_zi: (I - companion(a)^T) zi = b[1:] - a[1:] b[0]
+    double zi0, zi1;
     {
         const double m00 = 1.0 + q->a1, m01 = -1.0, m10 = q->a2, m11 = 1.0;
         const double r0 = q->b1 - q->a1 * q->b0, r1 = q->b2 - q->a2 * q->b0;
         const double det = m00 * m11 - m01 * m10;
-        q->zi0 = (r0 * m11 - m01 * r1) / det;
-        q->zi1 = (m00 * r1 - m10 * r0) / det;
+        zi0 = (r0 * m11 - m01 * r1) / det;
+        zi1 = (m00 * r1 - m10 * r0) / det;
     }
-    // state transition of transposed direct form II: z' = A z + B x, y = z1 + b0 x
-    const double A[4] = {-q->a1, 1.0, -q->a2, 0.0};
-    double P[4] = {1.0, 0.0, 0.0, 1.0};
-    double A14[4] = {1, 0, 0, 1};
+    // direct form I initial outputs equivalent to the transposed-form-II state (zi0, zi1) with
+    // x[-1] = x[-2] = 0:  -a1 y[-1] - a2 y[-2] = zi0,  -a2 y[-1] = zi1
+    q->yi0 = -zi1 / q->a2;
+    q->yi1 = (-zi0 + q->a1 * zi1 / q->a2) / q->a2;
+    // companion matrix of the output recursion: (y[n], y[n-1]) = C (y[n-1], y[n-2])
+    const double Cm[4] = {-q->a1, -q->a2, 1.0, 0.0};
+    double P[4] = {Cm[0], Cm[1], Cm[2], Cm[3]};       // C^(i+1)
+    double C14[4] = {1, 0, 0, 1};
     for (int i = 0; i < KW_L; ++i) {
-        q->g[i][0] = P[0];
-        q->g[i][1] = P[1];
-        if (i == KW_SLACK) memcpy(A14, P, sizeof P);
-        mat2_mul(A, P, P);
+        if (i < KW_SUBMAX) { q->g[i][0] = P[0]; q->g[i][1] = P[1]; }
+        if (i + 1 == KW_SLACK) memcpy(C14, P, sizeof P);
+        if (i + 1 == 16) memcpy(q->c16, P, sizeof P);
+        if (i + 1 == 17) memcpy(q->c17, P, sizeof P);
+        if (i + 1 < KW_L) mat2_mul(Cm, P, P);
     }
-    memcpy(q->phi[0], P, sizeof P);              // A^65
+    memcpy(q->phi[0], P, sizeof P);              // C^65
     for (int j = 1; j < 5; ++j) mat2_mul(q->phi[j - 1], q->phi[j - 1], q->phi[j]);
-    const double det = A14[0] * A14[3] - A14[1] * A14[2];
-    q->ainv[0] = A14[3] / det; q->ainv[1] = -A14[1] / det;
-    q->ainv[2] = -A14[2] / det; q->ainv[3] = A14[0] / det;
+    const double det = C14[0] * C14[3] - C14[1] * C14[2];
+    q->cinv[0] = C14[3] / det; q->cinv[1] = -C14[1] / det;
+    q->cinv[2] = -C14[2] / det; q->cinv[3] = C14[0] / det;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -34,23 +34,22 @@ struct TruePeakArgs {
 };
 
 template <int LOG2M>
-__global__ void __launch_bounds__(FftShape<LOG2M>::NT, (FftShape<LOG2M>::NT <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(256, 2)
 truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
     using S = FftShape<LOG2M>;
     constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
-    constexpr int RSTRIDE = TPF + TPF / 16;
     constexpr int WARPS_PER_FFT = (TPF + 31) / 32;
-    static_assert(TPF >= 32 && S::PINGPONG, "true-peak kernel needs whole warps per sub-FFT and two buffers");
+    static_assert(TPF >= 32 && S::NT == 256 && LOG2M <= 12, "true-peak kernel: whole warps per sub-FFT, local FFT variant");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* bufs = reinterpret_cast<float2*>(smem_raw);
-    float2* xs_all = bufs + (size_t)CONC * 2 * BUF;                // [CONC][M+1] spectrum
+    float2* bufs = reinterpret_cast<float2*>(smem_raw);                            // [CONC][BUF + M]
+    float2* xs_all = bufs + (size_t)CONC * (BUF + M);                              // [CONC][M+1] spectrum
     float* red_all = reinterpret_cast<float*>(xs_all + (size_t)CONC * (M + 1));   // [CONC][WARPS_PER_FFT]
 
     const int tid = threadIdx.x;
     const int g = tid / TPF;
     const int t = tid % TPF;
-    float2* buf0 = bufs + (size_t)g * 2 * BUF;
-    float2* buf1 = buf0 + BUF;
+    float2* X = bufs + (size_t)g * (BUF + M);
+    float2* Z = X + BUF;
     float2* Xs = xs_all + (size_t)g * (M + 1);
     float* red = red_all + g * WARPS_PER_FFT;
 
@@ -64,10 +63,10 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
         win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
-    StageTw<LOG2M> st;
-    load_stage_twiddles<LOG2M>(st, a.twM, t);
-    const int rbase = padi(t);
+    LocalTw<LOG2M> st;
+    load_local_twiddles<LOG2M>(st, a.twM, t);
     const float inv_m = 1.0f / (float)M;
+    auto nop = []() {};
 
     for (int r = 0; r < a.rounds; ++r) {
         const int f = f0 + r * CONC + g;
@@ -91,15 +90,15 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                 pk = fmaxf(pk, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
             }
         }
-        const float2* Z = fft_forward<LOG2M, false>(v, buf0, buf1, st, t, active);
+        fft_forward_local<LOG2M, false>(v, X, Z, st, t, active, nop);
         // untangle -> X[0..M] in Xs
         if (active) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
                 int u = (i < 8) ? t + i * TPF : M / 2;
                 if (i == 8 && t != 0) break;
-                float2 Zk = Z[padi(u)];
-                float2 Zm = Z[padi((M - u) & (M - 1))];
+                float2 Zk = Z[zaddr<LOG2M>(u)];
+                float2 Zm = Z[zaddr<LOG2M>((M - u) & (M - 1))];
                 float2 Xk, Xm;
                 rfft_pair(Zk, Zm, __ldg(a.twN + u), Xk, Xm);
                 Xs[u] = Xk;
@@ -133,28 +132,27 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                     float2 H = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
                     float2 O = cmul(H, make_float2(tw.x, -tw.y));
                     // c[k] = conj(E) - i conj(O) = (E.x - O.y, -E.y - O.x);  c[M-k] = E - iO = (E.x + O.y, E.y - O.x)
-                    buf1[padi(u)] = make_float2(E.x - O.y, -E.y - O.x);
-                    if (u != 0) buf1[padi(M - u)] = make_float2(E.x + O.y, E.y - O.x);
+                    Z[zaddr<LOG2M>(u)] = make_float2(E.x - O.y, -E.y - O.x);
+                    if (u != 0) Z[zaddr<LOG2M>(M - u)] = make_float2(E.x + O.y, E.y - O.x);
                 }
             }
-            __syncthreads();
+            __syncthreads();      // c[] complete; also: every thread is past the previous transform's X reads
             if (active) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = buf1[rbase + j * RSTRIDE];
+                for (int j = 0; j < 16; ++j) v[j] = Z[zaddr<LOG2M>(t + j * TPF)];
             }
-            fft_forward<LOG2M, true>(v, buf0, buf1, st, t, active);
+            fft_forward_local<LOG2M, true>(v, X, Z, st, t, active, nop);
             if (active) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) pko = fmaxf(pko, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
             }
-            __syncthreads();      // buf1 is rewritten by the next phase's prologue
         }
         pk = fmaxf(pk, pko * inv_m);
         // reduce over the sub-FFT's threads
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
         if ((t & 31) == 0) red[t >> 5] = pk;
-        __syncthreads();
+        __syncthreads();          // also orders the last transform's X reads before the next round's stage-1 store
         if (active && t == 0) {
             float m = red[0];
 #pragma unroll
@@ -162,14 +160,14 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
             double peak = (double)m;
             a.tp_out[(size_t)ch * a.n_frames + f] = (peak < 1e-10) ? -100.0 : 20.0 * log10(peak);
         }
-        // red[] and Xs[] are next written after the barriers of the next round's forward transform
+        // red[] is next written after several barriers of the next round
     }
 }
 
 template <int LOG2M>
 inline size_t truepeak_smem_bytes() {
     using S = FftShape<LOG2M>;
-    return (size_t)S::CONC * 2 * S::BUF * sizeof(float2) + (size_t)S::CONC * (S::M + 1) * sizeof(float2)
+    return (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) + (size_t)S::CONC * (S::M + 1) * sizeof(float2)
            + (size_t)S::CONC * ((S::TPF + 31) / 32) * sizeof(float) + 16;
 }
 

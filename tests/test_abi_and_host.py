@@ -118,23 +118,26 @@ def test_mel_bands_and_meter_coefficients_match_oracle(golden):
 
 
 def test_block_scan_formulation_of_filtfilt_matches_oracle():
-    """numpy emulation of kweight_kernel's algorithm (32 lanes x 65 samples, zero-state sweep,
-    Kogge-Stone scan with Phi^(2^j), homogeneous correction, A^-14 virtual start for the backward
-    pass) -- proves the scan tables build_biquad() derives are the right ones."""
+    """numpy emulation of kweight_kernel's algorithm (32 lanes x 65 samples, direct-form-I
+    zero-state sweep with the neighbour's input history, Kogge-Stone scan with Phi^(2^j),
+    homogeneous correction, C^-14 virtual start for the backward pass) -- proves the scan tables
+    build_biquad() derives are the right ones."""
     from omega4_b200 import tables
     L, NL, PAD, Wn = 65, 32, 9, 2048
     coef = tables.k_weighting_coeffs(48000)
 
     def biquad(b, a):
-        A = np.array([[-a[1], 1.0], [-a[2], 0.0]])
-        g = np.zeros((L, 2)); P = np.eye(2)
+        a1, a2 = a[1], a[2]
+        C = np.array([[-a1, -a2], [1.0, 0.0]])
+        g = np.zeros((L, 2)); P = C.copy()
         for i in range(L):
             g[i] = P[0]
-            if i == 14:
-                A14 = P.copy()
-            P = A @ P
+            if i + 1 < L:
+                P = C @ P
+        zi = O.lfilter_zi2(b, a)
+        yinit = np.array([-zi[1] / a2, (-zi[0] + a1 * zi[1] / a2) / a2])
         return dict(b=b, a=a, g=g, phi=[np.linalg.matrix_power(P, 2 ** j) for j in range(5)],
-                    ainv=np.linalg.inv(A14), zi=O.lfilter_zi2(b, a))
+                    cinv=np.linalg.inv(np.linalg.matrix_power(C, 14)), yinit=yinit)
 
     def one_pass(r, q, backward):
         b0, b1, b2 = q["b"]; a1, a2 = q["a"][1], q["a"][2]
@@ -142,18 +145,25 @@ def test_block_scan_formulation_of_filtfilt_matches_oracle():
         x0 = r[31, 50] if backward else r[0, 0]
         if backward:
             r[31, 51:] = 0.0
-        s_init = q["zi"] * x0
+        s_init = q["yinit"] * x0
         if backward:
-            s_init = q["ainv"] @ s_init
+            s_init = q["cinv"] @ s_init
+        xo = r.copy()
         e = np.zeros((NL, 2))
-        order = range(L - 1, -1, -1) if backward else range(L)
+        order = list(range(L - 1, -1, -1)) if backward else list(range(L))
         for l in range(NL):
-            z1 = z2 = 0.0
+            prev = l + 1 if backward else l - 1
+            if 0 <= prev < NL:
+                xm1, xm2 = (xo[prev, 0], xo[prev, 1]) if backward else (xo[prev, 64], xo[prev, 63])
+            else:
+                xm1 = xm2 = 0.0
+            y1 = y2 = 0.0
             for i in order:
-                x = r[l, i]; y = b0 * x + z1
-                z1 = -a1 * y + (b1 * x + z2); z2 = -a2 * y + b2 * x
+                x = r[l, i]
+                y = -a1 * y1 + (-a2 * y2 + (b0 * x + (b1 * xm1 + b2 * xm2)))
+                xm2, xm1, y2, y1 = xm1, x, y1, y
                 r[l, i] = y
-            e[l] = (z1, z2)
+            e[l] = (y1, y2)
         pos = 31 - np.arange(NL) if backward else np.arange(NL)
         v = e.copy()
         v[np.where(pos == 0)[0][0]] += q["phi"][0] @ s_init
