@@ -253,6 +253,21 @@ __device__ __forceinline__ float2* fft_forward(float2* v, float2* buf0, float2* 
 //   Z buffer (M float2, natural order, XOR swizzle zaddr()): conflict free for the final store
 //       (lanes vary in q and p) and for consecutive reads by the epilogue.
 // ---------------------------------------------------------------------------------------------
+// Synchronise the NTHREADS consecutive threads that own one sub-FFT ("group" index g inside the
+// CTA): a warp-level sync when the group fits in a warp, a named barrier when it spans 2..4
+// warps, the CTA barrier when the group is the whole 256-thread CTA.  Groups of different frames
+// never wait for each other.
+template <int NTHREADS>
+__device__ __forceinline__ void group_sync(int g) {
+    if (NTHREADS <= 32) {
+        __syncwarp();
+    } else if (NTHREADS < 256) {
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(NTHREADS) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
 template <int LOG2M>
 __host__ __device__ __forceinline__ constexpr int zaddr(int idx) {
     constexpr int G2 = (1 << LOG2M) / 256;
@@ -272,15 +287,17 @@ __device__ __forceinline__ void load_local_twiddles(LocalTw<LOG2M>& st, const fl
     st.s2.w4 = __ldg(twM + 4 * e); st.s2.w8 = __ldg(twM + 8 * e);
 }
 
-// On entry v[16] = z[t + j*M/16].  X, Z: this sub-FFT group's buffers.  Contains two
-// __syncthreads() (after the stage-1 store; after the final store unless KEEP_LAST_IN_REGS).
+// On entry v[16] = z[t + j*M/16].  X, Z: this sub-FFT group's buffers.  Contains two group
+// barriers (after the stage-1 store; after the final store unless KEEP_LAST_IN_REGS); all
+// threads of the group must call it together, groups are independent of each other.
 // MID is invoked by every thread right after the first barrier (used to overlap deferred work).
 // With KEEP_LAST_IN_REGS the final outputs stay in v[] (butterfly i of the last stage in
 // v[i*G2 .. i*G2+G2)) and nothing is written to Z.
 template <int LOG2M, bool KEEP_LAST_IN_REGS, typename Mid>
 __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* Z, const LocalTw<LOG2M>& st,
-                                                  int t, bool active, Mid&& mid) {
+                                                  int t, int g, bool active, Mid&& mid) {
     constexpr int M = 1 << LOG2M;
+    constexpr int TPF = M / 16;
     constexpr int G2 = M / 256;
     constexpr int S = 17 * G2;
     static_assert(LOG2M >= 8 && LOG2M <= 12, "local variant covers 256 .. 4096 complex points");
@@ -290,7 +307,7 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
 #pragma unroll
         for (int k = 0; k < 16; ++k) X[k * S + t] = v[k];
     }
-    __syncthreads();
+    group_sync<TPF>(g);
     mid();
     if (active) {
         const int q = t / G2, p = t % G2;
@@ -325,7 +342,7 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
             }
         }
     }
-    if (!KEEP_LAST_IN_REGS) __syncthreads();
+    if (!KEEP_LAST_IN_REGS) group_sync<TPF>(g);
 }
 
 // Untangle one (k, M-k) pair of the packed real transform.

@@ -157,7 +157,7 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
         }
         // the combine of the previous round runs right after this round's first barrier, which
         // also publishes the previous epilogue's magnitudes
-        fft_forward_local<LOG2M, false>(v, X, Z, st, t, active, [&]() {
+        fft_forward_local<LOG2M, false>(v, X, Z, st, t, g, active, [&]() {
             if (r > 0 && a.comb_out) {
                 const int fp = f - CONC;
                 if (fp < a.n_frames)
@@ -178,7 +178,7 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
             multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active);
     }
     if (a.comb_out) {
-        __syncthreads();
+        group_sync<TPF>(g);
         const int fl = f0 + (a.rounds - 1) * CONC + g;
         if (fl < a.n_frames)
             multires_combine<TPF>(a, ((a.rounds - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fl,

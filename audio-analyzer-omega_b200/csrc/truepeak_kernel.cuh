@@ -90,7 +90,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                 pk = fmaxf(pk, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
             }
         }
-        fft_forward_local<LOG2M, false>(v, X, Z, st, t, active, nop);
+        fft_forward_local<LOG2M, false>(v, X, Z, st, t, g, active, nop);
         // untangle -> X[0..M] in Xs
         if (active) {
 #pragma unroll
@@ -105,7 +105,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                 Xs[M - u] = Xm;
             }
         }
-        __syncthreads();
+        group_sync<TPF>(g);
         float pko = 0.f;                                  // phases 1..3, unnormalised (x M)
 #pragma unroll 1
         for (int p = 1; p <= 3; ++p) {
@@ -136,12 +136,12 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                     if (u != 0) Z[zaddr<LOG2M>(M - u)] = make_float2(E.x + O.y, E.y - O.x);
                 }
             }
-            __syncthreads();      // c[] complete; also: every thread is past the previous transform's X reads
+            group_sync<TPF>(g);      // c[] complete; also: every thread is past the previous transform's X reads
             if (active) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = Z[zaddr<LOG2M>(t + j * TPF)];
             }
-            fft_forward_local<LOG2M, true>(v, X, Z, st, t, active, nop);
+            fft_forward_local<LOG2M, true>(v, X, Z, st, t, g, active, nop);
             if (active) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) pko = fmaxf(pko, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
@@ -152,7 +152,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
         if ((t & 31) == 0) red[t >> 5] = pk;
-        __syncthreads();          // also orders the last transform's X reads before the next round's stage-1 store
+        group_sync<TPF>(g);          // also orders the last transform's X reads before the next round's stage-1 store
         if (active && t == 0) {
             float m = red[0];
 #pragma unroll
