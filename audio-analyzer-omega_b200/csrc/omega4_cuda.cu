@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -263,9 +264,9 @@ struct omega4_plan {
         cudaStream_t s = nullptr;
         DevBuf in, comb, met, lufs, tp, state, mag[OMEGA4_MAX_RES];
     };
-    static constexpr int N_SLOTS = 3;
+    static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
-    size_t host_chunk_bytes = (size_t)768 << 20;   // device bytes per slot
+    size_t host_chunk_bytes = (size_t)1536 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
     long long launches = 0;
     std::vector<KernelTime> times;
     size_t n_times = 0;
@@ -367,6 +368,10 @@ extern "C" omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int dev
     if (cudaSetDevice(device) != cudaSuccess) { fail(OMEGA4_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
     omega4_plan* p = new omega4_plan();
     p->device = device;
+    if (const char* e = getenv("OMEGA4_HOST_CHUNK_MB")) {           // tuning knob of the host-buffer pipeline
+        long mb = atol(e);
+        if (mb >= 16 && mb <= 16384) p->host_chunk_bytes = (size_t)mb << 20;
+    }
     if (plan_build(p, desc) != OMEGA4_OK) { std::string keep = g_err; omega4_plan_destroy(p); g_err = keep; return nullptr; }
     return p;
 }

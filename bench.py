@@ -135,8 +135,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="stereo streams per GPU (config[2]: 1024)")
     ap.add_argument("--seconds", type=int, default=60, help="seconds per stream (config[2]: 60)")
-    ap.add_argument("--e2e-streams", type=int, default=128, help="streams per host-buffer call of the e2e leg")
-    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="seconds per stream of the CPU baseline sample")
+    ap.add_argument("--e2e-streams", type=int, default=1024,
+                    help="streams per host-buffer call of the e2e leg (halved until the pinned buffers can be allocated)")
+    ap.add_argument("--cpu-seconds", type=float, default=60.0,
+                    help="seconds per stream of the CPU baseline sample (one stream per host core; 60 s = the workload's stream length)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -218,12 +220,30 @@ def main():
     e2e = None
     if not args.no_e2e:
         es = min(args.e2e_streams, n_streams)
+        try:                                          # never pin more than ~35 % of the free host memory per node
+            import psutil
+            avail = psutil.virtual_memory().available
+            per_stream = CHANNELS * (n_samples + n_hops * (T_BINS + N.N_METERS)) * 4
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            while es > 16 and es * per_stream * local_world > 0.35 * avail:
+                es //= 2
+        except Exception:
+            pass
+        hx = hcomb = hmet = None
+        while True:                                   # biggest pinned host batch this box can give us
+            ech = es * CHANNELS
+            try:
+                hx = torch.empty((ech, n_samples), dtype=torch.float32, pin_memory=True)
+                hcomb = torch.empty((ech, n_hops, T_BINS), dtype=torch.float32, pin_memory=True)
+                hmet = torch.empty((ech, n_hops, N.N_METERS), dtype=torch.float32, pin_memory=True)
+                break
+            except RuntimeError:
+                hx = hcomb = hmet = None
+                if es <= 16:
+                    raise
+                es //= 2
         calls = (n_streams + es - 1) // es
-        ech = es * CHANNELS
-        hx = torch.empty((ech, n_samples), dtype=torch.float32).pin_memory()
-        hx.copy_(x[:ech].cpu())
-        hcomb = torch.empty((ech, n_hops, T_BINS), dtype=torch.float32).pin_memory()
-        hmet = torch.empty((ech, n_hops, N.N_METERS), dtype=torch.float32).pin_memory()
+        hx.copy_(x[:ech])
 
         def e2e_step():
             for _ in range(calls):
