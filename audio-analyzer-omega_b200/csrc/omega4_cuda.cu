@@ -267,6 +267,10 @@ struct omega4_plan {
     static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
     size_t host_chunk_bytes = (size_t)1536 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
+    // device mode: the meter kernels (fp64 K-weighting, stats) run on a side stream so that they
+    // overlap the fp32 FFT kernels; fork/join with events on the caller's stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_tp = nullptr, ev_join = nullptr;
     long long launches = 0;
     std::vector<KernelTime> times;
     size_t n_times = 0;
@@ -395,6 +399,10 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
         if (sl.s) cudaStreamDestroy(sl.s);
     }
     for (auto& t : p->times) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_tp) cudaEventDestroy(p->ev_tp);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     cudaGetLastError();
     delete p;
 }
@@ -441,6 +449,76 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     if (timing) p->n_times = 0;
     if (((uintptr_t)x & 15) != 0 || (ch_stride % 4) != 0)
         return fail(OMEGA4_ERR_INVALID, "samples must be 16-byte aligned with ch_stride a multiple of 4");
+    const bool want_meters = meters || lufs || tp;
+    const bool concurrent = want_meters && !(flags & OMEGA4_FLAG_SERIAL);
+    cudaStream_t ms = s;                      // stream of the K-weighting + stats kernels
+    if (concurrent) {
+        if (!p->side) {
+            CK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_tp, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+        }
+        ms = p->side;
+        CK(cudaEventRecord(p->ev_fork, s));
+        CK(cudaStreamWaitEvent(ms, p->ev_fork, 0));
+    }
+    // ---- meters first: K-weighting on the meter stream, true peak on the caller's stream
+    if (want_meters) {
+        const size_t nser = (size_t)n_ch * n_hops * sizeof(double);
+        if (!lufs) { int rc = p->scratch_lufs.ensure(nser); if (rc) return rc; lufs = (double*)p->scratch_lufs.p; }
+        if (!tp) { int rc = p->scratch_tp.ensure(nser); if (rc) return rc; tp = (double*)p->scratch_tp.p; }
+        long long need = (long long)p->W - hist;
+        const int first_m = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
+        {
+            KweightArgs k;
+            memset(&k, 0, sizeof k);
+            k.x = x; k.x_is_f64 = 0; k.ch_stride = ch_stride; k.frame_stride = p->hop;
+            k.frame_off0 = (long long)p->hop - p->W;
+            k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
+            k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
+            k.hann = p->hann64; k.lufs_out = lufs; k.weighted_out = nullptr;
+            k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
+            Bracket b(p, ms, timing, "kweight_lufs");
+            int rc = launch_kweight(k, ms);
+            if (rc) return rc;
+        }
+        {
+            TruePeakArgs t;
+            memset(&t, 0, sizeof t);
+            t.x = x; t.x_is_f64 = 0; t.ch_stride = ch_stride; t.frame_stride = p->hop;
+            t.frame_off0 = (long long)p->hop - p->W;
+            t.n_ch = n_ch; t.n_frames = n_hops; t.first_frame = first_m;
+            t.rounds = default_rounds(n_hops, 4);
+            t.window = p->hann32; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
+            t.tp_out = tp;
+            Bracket b(p, s, timing, "true_peak");
+            int rc = launch_truepeak(t, s);
+            if (rc) return rc;
+        }
+        if (meters) {
+            if (concurrent) {
+                CK(cudaEventRecord(p->ev_tp, s));
+                CK(cudaStreamWaitEvent(ms, p->ev_tp, 0));
+            }
+            StatsArgs st;
+            memset(&st, 0, sizeof st);
+            st.lufs = lufs; st.tp = tp; st.n_ch = n_ch; st.n_frames = n_hops; st.first_frame = first_m;
+            st.gate = p->gate; st.out = meters;
+            st.fresh = (state == nullptr) || (flags & OMEGA4_FLAG_FRESH_METERS) ? 1 : 0;
+            if (!state) {
+                int rc = p->h_state.ensure((size_t)n_ch * ST_STATE * sizeof(double));
+                if (rc) return rc;
+                state = (double*)p->h_state.p;
+            }
+            st.state = state;
+            Bracket b(p, ms, timing, "meter_stats");
+            int rc = launch_stats(st, ms);
+            if (rc) return rc;
+        }
+        if (concurrent) CK(cudaEventRecord(p->ev_join, ms));
+    }
+    // ---- multi-resolution FFTs (+ fused combine) on the caller's stream
     const bool fused = p->disjoint;
     float* mag_ptr[OMEGA4_MAX_RES];
     int first[OMEGA4_MAX_RES];
@@ -487,55 +565,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c);
         CK(cudaGetLastError());
     }
-    if (meters || lufs || tp) {
-        const size_t nser = (size_t)n_ch * n_hops * sizeof(double);
-        if (!lufs) { int rc = p->scratch_lufs.ensure(nser); if (rc) return rc; lufs = (double*)p->scratch_lufs.p; }
-        if (!tp) { int rc = p->scratch_tp.ensure(nser); if (rc) return rc; tp = (double*)p->scratch_tp.p; }
-        long long need = (long long)p->W - hist;
-        const int first_m = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
-        {
-            KweightArgs k;
-            memset(&k, 0, sizeof k);
-            k.x = x; k.x_is_f64 = 0; k.ch_stride = ch_stride; k.frame_stride = p->hop;
-            k.frame_off0 = (long long)p->hop - p->W;
-            k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
-            k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
-            k.hann = p->hann64; k.lufs_out = lufs; k.weighted_out = nullptr;
-            k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
-            Bracket b(p, s, timing, "kweight_lufs");
-            int rc = launch_kweight(k, s);
-            if (rc) return rc;
-        }
-        {
-            TruePeakArgs t;
-            memset(&t, 0, sizeof t);
-            t.x = x; t.x_is_f64 = 0; t.ch_stride = ch_stride; t.frame_stride = p->hop;
-            t.frame_off0 = (long long)p->hop - p->W;
-            t.n_ch = n_ch; t.n_frames = n_hops; t.first_frame = first_m;
-            t.rounds = default_rounds(n_hops, 4);
-            t.window = p->hann32; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
-            t.tp_out = tp;
-            Bracket b(p, s, timing, "true_peak");
-            int rc = launch_truepeak(t, s);
-            if (rc) return rc;
-        }
-        if (meters) {
-            StatsArgs st;
-            memset(&st, 0, sizeof st);
-            st.lufs = lufs; st.tp = tp; st.n_ch = n_ch; st.n_frames = n_hops; st.first_frame = first_m;
-            st.gate = p->gate; st.out = meters;
-            st.fresh = (state == nullptr) || (flags & OMEGA4_FLAG_FRESH_METERS) ? 1 : 0;
-            if (!state) {
-                int rc = p->h_state.ensure((size_t)n_ch * ST_STATE * sizeof(double));
-                if (rc) return rc;
-                state = (double*)p->h_state.p;
-            }
-            st.state = state;
-            Bracket b(p, s, timing, "meter_stats");
-            int rc = launch_stats(st, s);
-            if (rc) return rc;
-        }
-    }
+    if (concurrent) CK(cudaStreamWaitEvent(s, p->ev_join, 0));
     return OMEGA4_OK;
 }
 
@@ -603,7 +633,7 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
                 rc = sl.mag[r].ensure(rows * p->res[r].bins * sizeof(float)); if (rc) return rc;
                 d_mag[r] = (float*)sl.mag[r].p; any_mag = true;
             }
-        const int fl = flags | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
+        const int fl = flags | OMEGA4_FLAG_SERIAL | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
         rc = analyze_device(p, sl.s, d_in + hist_al, dstride, nc, n_hops, (int)hist, d_comb, any_mag ? d_mag : nullptr,
                             d_met, d_lufs, d_tp, d_state, fl);
         if (rc) return rc;
