@@ -267,8 +267,8 @@ struct omega4_plan {
     static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
     size_t host_chunk_bytes = (size_t)1536 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
-    // device mode: the meter kernels (fp64 K-weighting, stats) run on a side stream so that they
-    // overlap the fp32 FFT kernels; fork/join with events on the caller's stream
+    // OMEGA4_FLAG_CONCURRENT_METERS: the K-weighting + stats kernels run on a side stream, forked /
+    // joined with events on the caller's stream
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_tp = nullptr, ev_join = nullptr;
     long long launches = 0;
@@ -450,7 +450,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     if (((uintptr_t)x & 15) != 0 || (ch_stride % 4) != 0)
         return fail(OMEGA4_ERR_INVALID, "samples must be 16-byte aligned with ch_stride a multiple of 4");
     const bool want_meters = meters || lufs || tp;
-    const bool concurrent = want_meters && !(flags & OMEGA4_FLAG_SERIAL);
+    const bool concurrent = want_meters && (flags & OMEGA4_FLAG_CONCURRENT_METERS);
     cudaStream_t ms = s;                      // stream of the K-weighting + stats kernels
     if (concurrent) {
         if (!p->side) {
@@ -633,7 +633,7 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
                 rc = sl.mag[r].ensure(rows * p->res[r].bins * sizeof(float)); if (rc) return rc;
                 d_mag[r] = (float*)sl.mag[r].p; any_mag = true;
             }
-        const int fl = flags | OMEGA4_FLAG_SERIAL | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
+        const int fl = (flags & ~OMEGA4_FLAG_CONCURRENT_METERS) | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
         rc = analyze_device(p, sl.s, d_in + hist_al, dstride, nc, n_hops, (int)hist, d_comb, any_mag ? d_mag : nullptr,
                             d_met, d_lufs, d_tp, d_state, fl);
         if (rc) return rc;

@@ -24,7 +24,7 @@ METER_STATE_DOUBLES = 8 + 3600 + 60
 N_METERS = 5
 FLAG_TIME_KERNELS = 1
 FLAG_FRESH_METERS = 2
-FLAG_SERIAL = 4
+FLAG_CONCURRENT_METERS = 4
 ABI_VERSION = 1
 
 #: every symbol include/omega4_cuda.h declares (checked by tests/test_abi_symbols.py)

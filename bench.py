@@ -202,10 +202,7 @@ def main():
     for name, ms in plan.kernel_times():
         ktimes[name] = ms
     launches = plan.launches - launches0
-    # one extra, untimed, fully serial step: clean per-kernel durations (no overlap between streams)
-    step(N.FLAG_TIME_KERNELS | N.FLAG_SERIAL)
-    torch.cuda.synchronize()
-    ktimes_serial = dict(plan.kernel_times())
+
     t_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -276,9 +273,7 @@ def main():
         peaks, peak_kind = measured_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         ch_hops = n_ch * n_hops
-        # dominant kernel = largest serial duration; its duration for the roofline is the one measured
-        # inside the timed region (where the meter kernels overlap the FFT kernels on a side stream)
-        dom = max(ktimes_serial, key=ktimes_serial.get) if ktimes_serial else None
+        dom = max(ktimes, key=ktimes.get) if ktimes else None
         roof = None
         if dom:
             # algorithmic bytes of the dominant kernel per launch: every input sample once + what it writes
@@ -315,7 +310,7 @@ def main():
             "roofline_fp32": {"flop_per_channel_hop": FLOP_PER_HOP, "achieved_tflops": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12,
                               "peak_tflops_nominal": FP32_PEAK_TFLOPS,
                               "frac": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12 / FP32_PEAK_TFLOPS},
-            "kernel_ms": ktimes, "kernel_ms_serial": ktimes_serial, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "kernel_ms": ktimes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
             "final_rows_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:

@@ -86,14 +86,14 @@ def main():
     met = torch.empty((n_ch, n_hops, 5), dtype=torch.float32, device="cuda")
     for it in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=N.FLAG_TIME_KERNELS | N.FLAG_FRESH_METERS)
+        plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=N.FLAG_TIME_KERNELS | N.FLAG_FRESH_METERS | N.FLAG_CONCURRENT_METERS)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         print(f"iter {it}: {dt*1e3:.1f} ms  -> {n_ch*n_hops/dt/1e6:.2f} M channel-hops/s, "
               f"{n_ch/2*n_hops*512/48000/dt:.0f} stereo stream-s/s")
     for name, ms in plan.kernel_times():
         print(f"   {name:20s} {ms:8.3f} ms (concurrent)")
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=N.FLAG_TIME_KERNELS | N.FLAG_FRESH_METERS | N.FLAG_SERIAL)
+    plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=N.FLAG_TIME_KERNELS | N.FLAG_FRESH_METERS)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"serial: {dt*1e3:.1f} ms")
     for name, ms in plan.kernel_times():
