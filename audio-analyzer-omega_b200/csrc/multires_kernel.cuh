@@ -48,9 +48,10 @@ struct ZSwizzled { __device__ static __forceinline__ int at(int i) { return zadd
 // Untangle + |X| * weight for the bins this thread owns: pairs u = t + i*TPF in [0, M/2), plus
 // u = M/2 handled by thread 0.  In fused mode (no mag/complex output) only the bins the combine
 // step needs are evaluated.
+// twn / bw: twN and per-bin weight tables (global via the read-only path, or a shared-memory copy)
 template <int LOG2M, typename ZA>
 __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const float2* Z, float* mags, int t,
-                                                  size_t row, bool active) {
+                                                  size_t row, bool active, const float2* twn, const float* bw) {
     using S = FftShape<LOG2M>;
     constexpr int M = S::M, TPF = S::TPF;
     const bool all_bins = (a.mag_out != nullptr) || (a.cplx_out != nullptr);
@@ -70,11 +71,11 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
         if (active) {
             const float2 Zk = Z[ZA::at(u)];
             const float2 Zm = Z[ZA::at((M - u) & (M - 1))];
-            const float2 w = __ldg(a.twN + u);
+            const float2 w = twn[u];
             rfft_pair(Zk, Zm, w, Xk, Xm);
             mk = cabs(Xk);
             mm = cabs(Xm);
-            if (a.binw) { mk *= __ldg(a.binw + k); mm *= __ldg(a.binw + km); }
+            if (bw) { mk *= bw[k]; mm *= bw[km]; }
         }
         if (mrow) { mrow[k] = mk; mrow[km] = mm; }
         if (crow) { crow[k] = Xk; crow[km] = Xm; }
@@ -84,19 +85,22 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
 }
 
 // np.interp segments of combine_results_optimized evaluated from the smem strip of magnitudes.
+struct CombTables { const int* idx; const int* lo; const float* frac; };
+
 template <int TPF>
-__device__ __forceinline__ void multires_combine(const MultiresArgs& a, const float* mags, int t, size_t row, bool active) {
+__device__ __forceinline__ void multires_combine(const MultiresArgs& a, const float* mags, int t, size_t row, bool active,
+                                                 const CombTables tb) {
     float* orow = a.comb_out + row * a.T;
     for (int j = t; j < a.n_tb; j += TPF) {
-        const int lo = __ldg(a.tb_lo + j);
+        const int lo = tb.lo[j];
         float val = 0.f;
         if (active && lo >= 0) {
             const float m0 = mags[lo - a.need_lo];
             const float m1 = mags[lo + 1 - a.need_lo];
-            const float vi = fmaf(m1 - m0, __ldg(a.tb_frac + j), m0);
+            const float vi = fmaf(m1 - m0, tb.frac[j], m0);
             val = (vi * a.wnum) / a.wden;
         }
-        orow[__ldg(a.tb_idx + j)] = val;
+        orow[tb.idx[j]] = val;
     }
 }
 
@@ -121,6 +125,25 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
     const int mstride = a.need_cnt > 0 ? a.need_cnt : 1;
     float* mags0 = mags_all + (size_t)g * mstride;
     float* mags1 = mags0 + (size_t)CONC * mstride;
+    // small read-only tables are staged in shared memory once per CTA: ncu showed the N = 1024
+    // kernel stalled 35 % of the time on their global (L1/L2) loads in the epilogue / combine
+    int* s_tb_idx = reinterpret_cast<int*>(mags_all + (size_t)2 * CONC * mstride);
+    int* s_tb_lo = s_tb_idx + a.n_tb;
+    float* s_tb_frac = reinterpret_cast<float*>(s_tb_lo + a.n_tb);
+    constexpr bool STAGE_TW = (LOG2M <= 10);
+    float2* s_twn = reinterpret_cast<float2*>(s_tb_frac + a.n_tb + ((3 * a.n_tb) & 1));     // 8-byte aligned
+    float* s_bw = reinterpret_cast<float*>(s_twn + (STAGE_TW ? M / 2 + 1 : 0));
+    for (int j = threadIdx.x; j < a.n_tb; j += 256) {
+        s_tb_idx[j] = __ldg(a.tb_idx + j); s_tb_lo[j] = __ldg(a.tb_lo + j); s_tb_frac[j] = __ldg(a.tb_frac + j);
+    }
+    if (STAGE_TW) {
+        for (int j = threadIdx.x; j <= M / 2; j += 256) s_twn[j] = __ldg(a.twN + j);
+        if (a.binw) for (int j = threadIdx.x; j <= M; j += 256) s_bw[j] = __ldg(a.binw + j);
+    }
+    __syncthreads();
+    const CombTables ctb{s_tb_idx, s_tb_lo, s_tb_frac};
+    const float2* twn = STAGE_TW ? s_twn : a.twN;
+    const float* bw = a.binw ? (STAGE_TW ? s_bw : a.binw) : nullptr;
 
     const int frames_per_cta = a.rounds * CONC;
     const int tiles_per_ch = (a.n_frames + frames_per_cta - 1) / frames_per_cta;
@@ -162,7 +185,7 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
                 const int fp = f - CONC;
                 if (fp < a.n_frames)
                     multires_combine<TPF>(a, ((r - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fp,
-                                          fp >= a.first_frame);
+                                          fp >= a.first_frame, ctb);
             }
         });
         // prefetch the next round's samples; they land while the epilogue runs
@@ -175,22 +198,25 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
             }
         }
         if (valid)
-            multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active);
+            multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active,
+                                                       twn, bw);
     }
     if (a.comb_out) {
         group_sync<TPF>(g);
         const int fl = f0 + (a.rounds - 1) * CONC + g;
         if (fl < a.n_frames)
             multires_combine<TPF>(a, ((a.rounds - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fl,
-                                  fl >= a.first_frame);
+                                  fl >= a.first_frame, ctb);
     }
 }
 
 template <int LOG2M>
-inline size_t multires_local_smem_bytes(int need_cnt) {
+inline size_t multires_local_smem_bytes(int need_cnt, int n_tb) {
     using S = FftShape<LOG2M>;
-    return (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) +
-           (size_t)2 * S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float);
+    size_t b = (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) +
+               (size_t)2 * S::CONC * (need_cnt > 0 ? need_cnt : 1) * sizeof(float) + (size_t)(3 * n_tb + 2) * 4;
+    if (LOG2M <= 10) b += (size_t)(S::M / 2 + 1) * sizeof(float2) + (size_t)(S::M + 1) * sizeof(float);
+    return b + 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,9 +280,9 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
             }
         }
         const size_t row = (size_t)ch * a.n_frames + (valid ? f : 0);
-        if (valid) multires_epilogue<LOG2M, ZPadded>(a, Z, mags, t, row, active);
+        if (valid) multires_epilogue<LOG2M, ZPadded>(a, Z, mags, t, row, active, a.twN, a.binw);
         __syncthreads();
-        if (valid && a.comb_out) multires_combine<TPF>(a, mags, t, row, active);
+        if (valid && a.comb_out) multires_combine<TPF>(a, mags, t, row, active, CombTables{a.tb_idx, a.tb_lo, a.tb_frac});
         // No second barrier needed: every thread has finished reading Z before the barrier above,
         // and the next epilogue's writes to mags are separated from this combine's reads by the
         // barriers inside fft_forward.

@@ -95,7 +95,7 @@ static int launch_multires_t(const MultiresArgs& a, cudaStream_t s) {
     if (grid <= 0) return OMEGA4_OK;
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "multires grid too large");
     if constexpr (L <= 12) {
-        const size_t smem = multires_local_smem_bytes<L>(a.need_cnt);
+        const size_t smem = multires_local_smem_bytes<L>(a.need_cnt, a.n_tb);
         CK(cudaFuncSetAttribute(multires_local_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         multires_local_kernel<L><<<(unsigned)grid, 256, smem, s>>>(a);
     } else {
