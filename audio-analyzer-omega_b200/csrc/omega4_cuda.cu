@@ -8,11 +8,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include "blockdft_kernel.cuh"
 #include "fft_core.cuh"
 #include "kweight_kernel.cuh"
 #include "misc_kernels.cuh"
@@ -226,6 +228,15 @@ struct ResInfo {
     float* tb_frac = nullptr;
     int need_lo = 0, need_cnt = 0;
     Twiddles tw;
+    int sparse = -1;              // index into omega4_plan::sp when the hop-block partial DFT path serves it
+};
+
+// A resolution whose fused output needs only a few FFT bins (blockdft_kernel.cuh)
+struct SparseRes {
+    int r = 0, nk = 0, nt = 0, B = 0, col0 = 0;
+    float2* T = nullptr;          // [nk][B][nt]
+    float* kw = nullptr;          // [nk]
+    int* tb_pos = nullptr;        // [n_tb]
 };
 
 struct DevBuf {
@@ -256,13 +267,16 @@ struct omega4_plan {
     float* hann32 = nullptr;
     KwBiquad kw[2];
     Twiddles tw_meter;
-    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES];
+    int sp_n = 0, sp_bn = 0;      // sparse resolutions, padded column count of their shared GEMM
+    SparseRes sp[OMEGA4_MAX_RES];
+    float* sp_E = nullptr;        // [hop][sp_bn]
+    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q;
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
     // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
     // that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
     struct Slot {
         cudaStream_t s = nullptr;
-        DevBuf in, comb, met, lufs, tp, state, mag[OMEGA4_MAX_RES];
+        DevBuf in, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
     };
     static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
@@ -280,6 +294,12 @@ static int upload(void** dst, const void* src, size_t bytes) {
     CK(cudaMalloc(dst, bytes ? bytes : 1));
     if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     return OMEGA4_OK;
+}
+
+static size_t boff_of(const omega4_plan_desc* d, int r) {
+    size_t o = 0;
+    for (int i = 0; i < r; ++i) o += (size_t)d->fft_sizes[i] / 2 + 1;
+    return o;
 }
 
 static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
@@ -349,6 +369,108 @@ static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
         rc = upload((void**)&ri.tb_lo, lo[r].data(), lo[r].size() * sizeof(int)); if (rc) return rc;
         rc = upload((void**)&ri.tb_frac, fr[r].data(), fr[r].size() * sizeof(float)); if (rc) return rc;
     }
+    // hop-block partial DFT path (blockdft_kernel.cuh) for resolutions whose combine segments read
+    // only a few FFT bins and whose window is a short cosine sum
+    if (p->disjoint && (d->hop % BD_KC) == 0) {
+        int order[OMEGA4_MAX_RES];
+        for (int r = 0; r < d->n_res; ++r) order[r] = r;
+        for (int i = 0; i < d->n_res; ++i)                 // largest transform first
+            for (int j = i + 1; j < d->n_res; ++j)
+                if (p->res[order[j]].n > p->res[order[i]].n) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+        std::vector<std::vector<float>> ecols;             // per accepted resolution: [hop][2 nk nt]
+        int cols = 0;
+        size_t woff2[OMEGA4_MAX_RES];
+        { size_t o = 0; for (int r = 0; r < d->n_res; ++r) { woff2[r] = o; o += d->fft_sizes[r]; } }
+        for (int oi = 0; oi < d->n_res; ++oi) {
+            const int r = order[oi];
+            ResInfo& ri = p->res[r];
+            const int N = ri.n, H = d->hop;
+            if (N % H != 0 || N / H < 2 || N / H > 64) continue;
+            std::vector<int> bins;
+            for (int l : lo[r]) if (l >= 0) { bins.push_back(l); bins.push_back(l + 1); }
+            std::sort(bins.begin(), bins.end());
+            bins.erase(std::unique(bins.begin(), bins.end()), bins.end());
+            if (bins.empty()) continue;
+            // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
+            const float* w = d->windows + woff2[r];
+            const double phi = 6.283185307179586476925287 / (double)(N - 1);
+            double G[3][4] = {{0}};
+            for (int i = 0; i < N; ++i) {
+                const double c[3] = {1.0, cos(phi * i), cos(2.0 * phi * i)};
+                for (int u = 0; u < 3; ++u) { for (int v = 0; v < 3; ++v) G[u][v] += c[u] * c[v]; G[u][3] += c[u] * (double)w[i]; }
+            }
+            bool singular = false;
+            for (int u = 0; u < 3 && !singular; ++u) {        // Gauss-Jordan with partial pivoting
+                int piv = u;
+                for (int v = u + 1; v < 3; ++v) if (fabs(G[v][u]) > fabs(G[piv][u])) piv = v;
+                if (fabs(G[piv][u]) < 1e-9) { singular = true; break; }
+                if (piv != u) for (int c2 = 0; c2 < 4; ++c2) { double t = G[u][c2]; G[u][c2] = G[piv][c2]; G[piv][c2] = t; }
+                for (int v = 0; v < 3; ++v) {
+                    if (v == u) continue;
+                    const double f = G[v][u] / G[u][u];
+                    for (int c2 = 0; c2 < 4; ++c2) G[v][c2] -= f * G[u][c2];
+                }
+            }
+            if (singular) continue;
+            double am[3] = {G[0][3] / G[0][0], G[1][3] / G[1][1], G[2][3] / G[2][2]};
+            double resid = 0.0;
+            for (int i = 0; i < N; ++i) {
+                const double fit = am[0] + am[1] * cos(phi * i) + am[2] * cos(2.0 * phi * i);
+                resid = fmax(resid, fabs(fit - (double)w[i]));
+            }
+            if (resid > 1.5e-7) continue;                     // not a cosine-sum window: keep the FFT path
+            int tm[5]; double tc[5]; int nt = 0;
+            tm[nt] = 0; tc[nt] = am[0]; ++nt;
+            for (int m = 1; m <= 2; ++m)
+                if (fabs(am[m]) > 1e-9) { tm[nt] = m; tc[nt] = 0.5 * am[m]; ++nt; tm[nt] = -m; tc[nt] = 0.5 * am[m]; ++nt; }
+            const int nk = (int)bins.size();
+            const int rc_cols = 2 * nk * nt;
+            // GEMM FMAs per hop must be well below the FFT's ~2.5 N log2 N instructions
+            if ((double)rc_cols * H * 2.0 > 2.5 * N * (ri.log2m + 1)) continue;
+            if (cols + rc_cols > 128) continue;
+            SparseRes& sp = p->sp[p->sp_n];
+            sp.r = r; sp.nk = nk; sp.nt = nt; sp.B = N / H; sp.col0 = cols;
+            std::vector<float> ec((size_t)H * rc_cols);
+            std::vector<float2> T((size_t)nk * sp.B * nt);
+            std::vector<float> kw(nk);
+            const double two_pi = 6.283185307179586476925287;
+            for (int ki = 0; ki < nk; ++ki) {
+                kw[ki] = d->bin_weights ? d->bin_weights[boff_of(d, r) + bins[ki]] : 1.f;
+                for (int t = 0; t < nt; ++t) {
+                    const double th = tm[t] * phi - two_pi * (double)bins[ki] / (double)N;
+                    for (int n2 = 0; n2 < H; ++n2) {
+                        const double ang = fmod(th * n2, two_pi);
+                        ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t)] = (float)cos(ang);
+                        ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t) + 1] = (float)sin(ang);
+                    }
+                    for (int b = 0; b < sp.B; ++b) {
+                        const double ang = fmod(th * (double)H * b, two_pi);
+                        T[((size_t)ki * sp.B + b) * nt + t] = make_float2((float)(tc[t] * cos(ang)), (float)(tc[t] * sin(ang)));
+                    }
+                }
+            }
+            std::vector<int> pos(idx[r].size(), -1);
+            for (size_t j = 0; j < lo[r].size(); ++j)
+                if (lo[r][j] >= 0) pos[j] = (int)(std::lower_bound(bins.begin(), bins.end(), lo[r][j]) - bins.begin());
+            int rc = upload((void**)&sp.T, T.data(), T.size() * sizeof(float2)); if (rc) return rc;
+            rc = upload((void**)&sp.kw, kw.data(), kw.size() * sizeof(float)); if (rc) return rc;
+            rc = upload((void**)&sp.tb_pos, pos.data(), pos.size() * sizeof(int)); if (rc) return rc;
+            ri.sparse = p->sp_n++;
+            ecols.push_back(std::move(ec));
+            cols += rc_cols;
+        }
+        if (p->sp_n > 0) {
+            p->sp_bn = cols <= 32 ? 32 : (cols <= 64 ? 64 : 128);
+            std::vector<float> E((size_t)d->hop * p->sp_bn, 0.f);
+            for (int si = 0; si < p->sp_n; ++si) {
+                const SparseRes& sp = p->sp[si];
+                const int rc_cols = 2 * sp.nk * sp.nt;
+                for (int n2 = 0; n2 < d->hop; ++n2)
+                    memcpy(&E[(size_t)n2 * p->sp_bn + sp.col0], &ecols[si][(size_t)n2 * rc_cols], rc_cols * sizeof(float));
+            }
+            int rc = upload((void**)&p->sp_E, E.data(), E.size() * sizeof(float)); if (rc) return rc;
+        }
+    }
     // meters
     int rc = upload((void**)&p->hann64, d->meter_hann, (size_t)p->W * sizeof(double)); if (rc) return rc;
     std::vector<float> h32(p->W);
@@ -390,11 +512,14 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     }
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
     cudaFree(p->hann64); cudaFree(p->hann32);
-    p->scratch_lufs.release(); p->scratch_tp.release();
+    p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release();
+    for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(p->sp[i].T); cudaFree(p->sp[i].kw); cudaFree(p->sp[i].tb_pos); }
+    cudaFree(p->sp_E);
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
     for (auto& sl : p->slots) {
         sl.in.release(); sl.comb.release(); sl.met.release(); sl.lufs.release(); sl.tp.release(); sl.state.release();
+        sl.q.release();
         for (auto& m : sl.mag) m.release();
         if (sl.s) cudaStreamDestroy(sl.s);
     }
@@ -442,9 +567,30 @@ extern "C" int omega4_plan_kernel_times(omega4_plan* p, char* names, float* ms, 
 // ------------------------------------------------------------------------------------------
 // the hot path on device pointers
 // ------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_blockdft_gemm_t(const BlockDftGemmArgs& a, cudaStream_t s) {
+    const size_t smem = blockdft_gemm_smem_bytes<BN>();
+    CK(cudaFuncSetAttribute(blockdft_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (long long)((a.nb + BD_BM - 1) / BD_BM) * a.n_ch;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
+    blockdft_gemm_kernel<BN><<<(unsigned)grid, BD_THREADS, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+static int launch_blockdft_gemm(int bn, const BlockDftGemmArgs& a, cudaStream_t s) {
+    if (a.nb <= 0 || a.n_ch <= 0) return OMEGA4_OK;
+    switch (bn) {
+        case 32: return launch_blockdft_gemm_t<32>(a, s);
+        case 64: return launch_blockdft_gemm_t<64>(a, s);
+        case 128: return launch_blockdft_gemm_t<128>(a, s);
+    }
+    return fail(OMEGA4_ERR_INVALID, "bad blockdft column tile");
+}
+
 static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long long ch_stride, int n_ch,
                           int n_hops, int hist, float* combined, float* const* mags, float* meters,
-                          double* lufs, double* tp, double* state, int flags) {
+                          double* lufs, double* tp, double* state, int flags, DevBuf* qbuf) {
     const bool timing = (flags & OMEGA4_FLAG_TIME_KERNELS) != 0;
     if (timing) p->n_times = 0;
     if (((uintptr_t)x & 15) != 0 || (ch_stride % 4) != 0)
@@ -522,6 +668,13 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     const bool fused = p->disjoint;
     float* mag_ptr[OMEGA4_MAX_RES];
     int first[OMEGA4_MAX_RES];
+    bool use_sparse[OMEGA4_MAX_RES] = {false};
+    bool any_sparse = false;
+    for (int r = 0; r < p->n_res; ++r) {
+        use_sparse[r] = combined && fused && p->res[r].sparse >= 0 && !(mags && mags[r]) &&
+                        !(flags & OMEGA4_FLAG_NO_BLOCKDFT);
+        any_sparse = any_sparse || use_sparse[r];
+    }
     for (int r = 0; r < p->n_res; ++r) {
         ResInfo& ri = p->res[r];
         // resolution r is filled once hist + (k+1) hop >= N
@@ -534,6 +687,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             mag_ptr[r] = (float*)p->scratch_mag[r].p;
         }
         if (!combined && !mag_ptr[r]) continue;
+        if (use_sparse[r]) continue;                      // served by the hop-block partial DFT below
         MultiresArgs a;
         memset(&a, 0, sizeof a);
         a.x = x; a.ch_stride = ch_stride; a.frame_stride = p->hop; a.frame_off0 = (long long)p->hop - ri.n;
@@ -550,6 +704,47 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         Bracket b(p, s, timing, name);
         int rc = launch_multires(ri.log2m, a, s);
         if (rc) return rc;
+    }
+    if (any_sparse) {
+        // one GEMM over the hop blocks serves every sparse resolution; then one assembly per resolution
+        int j0 = 1 << 30;
+        for (int r = 0; r < p->n_res; ++r)
+            if (use_sparse[r]) { const int j = first[r] + 1 - p->sp[p->res[r].sparse].B; if (j < j0) j0 = j; }
+        const int nb = n_hops - j0;
+        const float* Q = nullptr;
+        if (nb > 0) {
+            int rc = qbuf->ensure((size_t)n_ch * nb * p->sp_bn * sizeof(float));
+            if (rc) return rc;
+            BlockDftGemmArgs g;
+            memset(&g, 0, sizeof g);
+            g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
+            g.E = p->sp_E; g.Q = (float*)qbuf->p;
+            Q = g.Q;
+            Bracket b(p, s, timing, "blockdft_gemm");
+            rc = launch_blockdft_gemm(p->sp_bn, g, s);
+            if (rc) return rc;
+        }
+        for (int r = 0; r < p->n_res; ++r) {
+            if (!use_sparse[r]) continue;
+            const ResInfo& ri = p->res[r];
+            const SparseRes& sp = p->sp[ri.sparse];
+            BlockDftAsmArgs a;
+            memset(&a, 0, sizeof a);
+            a.Q = Q; a.qs = p->sp_bn; a.col0 = sp.col0; a.nb = nb > 0 ? nb : 0; a.j0 = j0;
+            a.nk = sp.nk; a.nt = sp.nt; a.B = sp.B; a.T = sp.T; a.kw = sp.kw;
+            a.n_ch = n_ch; a.n_frames = n_hops; a.first_frame = first[r];
+            a.comb_out = combined; a.Tbins = p->T; a.n_tb = ri.n_tb; a.tb_idx = ri.tb_idx; a.tb_pos = sp.tb_pos;
+            a.tb_frac = ri.tb_frac; a.wnum = ri.weight; a.wden = ri.weight;
+            const size_t smem = blockdft_assemble_smem_bytes(sp.nk, sp.nt, sp.B);
+            CK(cudaFuncSetAttribute(blockdft_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long grid = (long long)((n_hops + BD_FA - 1) / BD_FA) * n_ch;
+            if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft assemble grid too large");
+            char name[32];
+            snprintf(name, sizeof name, "blockdft_asm_%d", ri.n);
+            Bracket b(p, s, timing, name);
+            blockdft_assemble_kernel<<<(unsigned)grid, 256, smem, s>>>(a);
+            CK(cudaGetLastError());
+        }
     }
     if (combined && !fused) {
         CombineArgs c;
@@ -579,7 +774,7 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
     cudaStream_t s = (cudaStream_t)stream;
     if (mem == OMEGA4_MEM_DEVICE)
         return analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
-                              lufs_inst, tp_db, meter_state, flags);
+                              lufs_inst, tp_db, meter_state, flags, &p->scratch_q);
     if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
 
     // ---- host buffers: channel chunks pipelined over private streams (H2D | kernels | D2H overlap)
@@ -590,6 +785,7 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
     const long long dstride = (hist_al + new_len + 3) / 4 * 4;
     size_t per_ch = (size_t)dstride * sizeof(float) + (size_t)n_hops * 2 * sizeof(double) + ST_STATE * sizeof(double);
     if (combined) per_ch += (size_t)n_hops * p->T * sizeof(float);
+    if (combined && p->sp_n > 0) per_ch += (size_t)(n_hops + 64) * p->sp_bn * sizeof(float);
     if (meters) per_ch += (size_t)n_hops * 5 * sizeof(float);
     bool want_mag[OMEGA4_MAX_RES] = {false};
     for (int r = 0; r < p->n_res; ++r) {
@@ -635,7 +831,7 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
             }
         const int fl = (flags & ~OMEGA4_FLAG_CONCURRENT_METERS) | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
         rc = analyze_device(p, sl.s, d_in + hist_al, dstride, nc, n_hops, (int)hist, d_comb, any_mag ? d_mag : nullptr,
-                            d_met, d_lufs, d_tp, d_state, fl);
+                            d_met, d_lufs, d_tp, d_state, fl, &sl.q);
         if (rc) return rc;
         const size_t r0 = (size_t)c0 * n_hops;
         if (combined) CK(cudaMemcpyAsync(combined + r0 * p->T, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, sl.s));

@@ -278,8 +278,9 @@ def main():
         if dom:
             # algorithmic bytes of the dominant kernel per launch: every input sample once + what it writes
             out_bytes = {"multires_fft_8192": 6 * 4, "multires_fft_4096": 20 * 4, "multires_fft_2048": 102 * 4,
-                         "multires_fft_1024": 384 * 4, "true_peak": 8, "kweight_lufs": 8, "meter_stats": 20}.get(dom, 0)
-            in_bytes = 16 if dom == "meter_stats" else HOP * 4
+                         "multires_fft_1024": 384 * 4, "true_peak": 8, "kweight_lufs": 8, "meter_stats": 20,
+                         "blockdft_gemm": 128 * 4, "blockdft_asm_8192": 6 * 4}.get(dom, 0)
+            in_bytes = 16 if dom == "meter_stats" else (128 * 4 if dom.startswith("blockdft_asm") else HOP * 4)
             alg = ch_hops * (in_bytes + out_bytes)
             ach = alg / (ktimes[dom] / 1e3) / 1e9
             traffic = None

@@ -46,6 +46,9 @@ extern "C" {
                                                     stream, concurrently with the FFT kernels (helps small batches
                                                     that under-fill the GPU; measured slower at 2048 channels) */
 
+#define OMEGA4_FLAG_NO_BLOCKDFT 8                /* evaluate every resolution with the full FFT kernel even where the fused
+                                                    output needs only a few bins (default: hop-block partial DFT there) */
+
 typedef struct omega4_plan omega4_plan;
 
 /* Everything that defines the reference's behaviour is DATA computed on the host with the

@@ -165,6 +165,81 @@ def test_multires_96k_six_resolutions(golden):
     p.close()
 
 
+# ------------------------------------------------------------------ hop-block partial DFT (fused, few-bin resolutions)
+def _kernel_names(plan):
+    return [n for n, _ in plan.kernel_times()]
+
+
+def test_blockdft_path_matches_golden_and_full_fft(plan, golden):
+    """Fused output only (no magnitudes): N = 8192 feeds 5 target bins from 10 FFT bins, so the
+    library evaluates it as hop-block partial DFTs (blockdft_kernel.cuh).  Same golden vectors, and
+    the full-FFT evaluation of the same call (OMEGA4_FLAG_NO_BLOCKDFT) must agree."""
+    from omega4_b200 import _native as N
+    g = golden("multires_baseline.npz")
+    out = plan.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+    names = _kernel_names(plan)
+    assert "blockdft_gemm" in names and "blockdft_asm_8192" in names and "multires_fft_8192" not in names
+    assert "multires_fft_4096" in names
+    comb = out["combined"][0]
+    assert np.array_equal(comb == 0, g["combined"] == 0)
+    assert_spectrum_close(comb, g["combined"], TOL_DB, label="blockdft combined")
+    full = plan.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | N.FLAG_NO_BLOCKDFT)
+    names = _kernel_names(plan)
+    assert "multires_fft_8192" in names and "blockdft_gemm" not in names
+    assert np.array_equal(full["combined"][0] == 0, comb == 0)
+    scale = full["combined"][0].max(axis=1, keepdims=True) + 1e-20
+    assert (np.abs(full["combined"][0] - comb) / scale).max() < 2e-6
+    assert np.array_equal(full["combined"][0][:, 6:], comb[:, 6:])      # other resolutions untouched
+
+
+def test_blockdft_96k_default_and_window_variants(golden):
+    from omega4_b200 import _native as N
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS, DEFAULT_CONFIGS
+    # 96 kHz, six resolutions: 32768 and 16384 share one GEMM
+    g = golden("multires_96k.npz")
+    cfg = [(tuple(r), int(n), int(h), float(w), "blackman") for r, n, h, w in
+           zip(g["cfg_ranges"], g["cfg_sizes"], g["cfg_hops"], g["cfg_weights"])]
+    p = AnalysisPlan(96000, cfg, 512)
+    out = p.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+    names = _kernel_names(p)
+    assert "blockdft_asm_32768" in names and "blockdft_asm_16384" in names and "multires_fft_32768" not in names
+    assert_spectrum_close(out["combined"][0, 60:], g["combined_tail"], TOL_DB, label="96k blockdft")
+    assert np.array_equal(out["combined"][0, 60:] == 0, g["combined_tail"] == 0)
+    p.close()
+    # reference default sizes, T = 1024: 4096 feeds 10 target bins from 20 FFT bins = 200 GEMM columns,
+    # more than the FFT costs -> stays on the FFT kernel; T = 512 halves that and qualifies
+    g = golden("multires_default.npz")
+    p = AnalysisPlan(48000, DEFAULT_CONFIGS, 1024)
+    out = p.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+    assert "blockdft_gemm" not in _kernel_names(p)
+    assert np.array_equal(out["combined"][0] == 0, g["combined"] == 0)
+    assert_spectrum_close(out["combined"][0], g["combined"], TOL_DB, label="default blockdft")
+    p.close()
+    # rectangular ('hann' quirk) and hamming windows are cosine sums too
+    g = golden("multires_windows.npz")
+    wts = [str(w) for w in g["window_types"]]
+    cfg = [(c[0], c[1], c[2], c[3], wt) for c, wt in zip(BASELINE_CONFIGS, wts)]
+    x = golden("multires_baseline.npz")["x"][: int(g["n_samples"])]
+    p = AnalysisPlan(48000, cfg, 512)
+    out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+    assert "blockdft_gemm" in _kernel_names(p)
+    assert_spectrum_close(out["combined"][0, 23], g["combined_h23"], TOL_DB, label="window variants blockdft")
+    p.close()
+    # a window that is NOT a cosine sum keeps the FFT path
+    rng = np.random.default_rng(5)
+    wins = [np.blackman(c[1]).astype(np.float32) for c in BASELINE_CONFIGS]
+    wins[0] = (wins[0] * (1 + 0.01 * rng.standard_normal(8192))).astype(np.float32)
+    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512, windows=wins)
+    out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+    assert "blockdft_gemm" not in _kernel_names(p) and "multires_fft_8192" in _kernel_names(p)
+    mr = O.OracleMultiResFFT(48000, 20000, list(O.BASELINE_CONFIGS))
+    mr.windows[0] = wins[0]
+    for k in range(24):
+        res = mr.process_audio_chunk(x[k * HOP:(k + 1) * HOP])
+    assert_spectrum_close(out["combined"][0, 23], mr.combine(res, 512)[0], TOL_DB, label="custom window")
+    p.close()
+
+
 # ------------------------------------------------------------------ meters
 def test_meters_stream_golden(plan, golden):
     g = golden("meters_stream.npz")
