@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "bars_kernel.cuh"
 #include "blockdft_kernel.cuh"
 #include "fft_core.cuh"
 #include "kweight_kernel.cuh"
@@ -1093,5 +1094,101 @@ extern "C" int omega4_synth_fill(int device, void* stream, float* out_device, in
     synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_device, rows, n_channels, n_samples, row_stride, first_stream,
                                                          (double)sample_rate, clip_s);
     CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// application post-processing: combined spectrum -> band_values (omega4_main.py:992-1056)
+// ------------------------------------------------------------------------------------------
+struct omega4_bars {
+    int device = 0, T = 0, n_valid = 0, p_lo = 0, normalize_max = 0;
+    float p_frac = 0.f, scale = 0.8f;
+    int* bands = nullptr; float* gain = nullptr; float* sf = nullptr; float* sfc = nullptr;
+    DevBuf h_spec, h_out, h_peak, h_state;
+};
+
+extern "C" omega4_bars* omega4_bars_create(const omega4_bars_desc* d, int device) {
+    if (!d || !d->bands || d->spectrum_len < 2 || d->n_bars < 1 || d->percentile < 0 || d->percentile > 100) {
+        fail(OMEGA4_ERR_INVALID, "bad bars descriptor"); return nullptr;
+    }
+    if (omega4_device_count() == 0) { fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(OMEGA4_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    omega4_bars* b = new omega4_bars();
+    b->device = device; b->T = d->spectrum_len; b->scale = d->scale; b->normalize_max = d->normalize_max;
+    int nv = 0;
+    for (int i = 0; i < d->n_bars; ++i) {
+        const int s = d->bands[2 * i], e = d->bands[2 * i + 1];
+        if (s < 0 || e < s) { delete b; fail(OMEGA4_ERR_INVALID, "bad band table"); return nullptr; }
+        if (e > d->spectrum_len) break;                            // omega4_main.py:1012-1013
+        ++nv;
+    }
+    if (nv < 1 || nv > 2048) { delete b; fail(OMEGA4_ERR_UNSUPPORTED, "1..2048 bands must fit the spectrum"); return nullptr; }
+    b->n_valid = nv;
+    // np.percentile, method='linear': virtual index q/100 (n-1)
+    const double vi = d->percentile / 100.0 * (d->spectrum_len - 1);
+    b->p_lo = (int)floor(vi);
+    if (b->p_lo > d->spectrum_len - 2) b->p_lo = d->spectrum_len - 2;
+    b->p_frac = (float)(vi - b->p_lo);
+    std::vector<float> sf(nv), sfc(nv);
+    if (d->smooth) for (int i = 0; i < nv; ++i) { sf[i] = (float)d->smooth[i]; sfc[i] = (float)(1.0 - d->smooth[i]); }
+    bool ok = upload((void**)&b->bands, d->bands, (size_t)nv * 2 * sizeof(int)) == OMEGA4_OK;
+    if (ok && d->gain) ok = upload((void**)&b->gain, d->gain, (size_t)b->T * sizeof(float)) == OMEGA4_OK;
+    if (ok && d->smooth) ok = upload((void**)&b->sf, sf.data(), nv * sizeof(float)) == OMEGA4_OK &&
+                              upload((void**)&b->sfc, sfc.data(), nv * sizeof(float)) == OMEGA4_OK;
+    if (!ok) { std::string keep = g_err; omega4_bars_destroy(b); g_err = keep; return nullptr; }
+    return b;
+}
+
+extern "C" void omega4_bars_destroy(omega4_bars* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaFree(b->bands); cudaFree(b->gain); cudaFree(b->sf); cudaFree(b->sfc);
+    b->h_spec.release(); b->h_out.release(); b->h_peak.release(); b->h_state.release();
+    cudaGetLastError();
+    delete b;
+}
+
+extern "C" int omega4_bars_count(const omega4_bars* b) { return b ? b->n_valid : 0; }
+
+extern "C" int omega4_bars_run(omega4_bars* b, void* stream, int mem, const float* spectrum, int n_ch, int n_hops,
+                               float* state, int fresh, float* band_values, float* peak_values) {
+    if (!b || !spectrum || !band_values || n_ch < 0 || n_hops < 0) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_ch == 0 || n_hops == 0) return OMEGA4_OK;
+    CK(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t rows = (size_t)n_ch * n_hops;
+    BarsArgs a;
+    memset(&a, 0, sizeof a);
+    a.T = b->T; a.n_ch = n_ch; a.n_hops = n_hops; a.n_valid = b->n_valid; a.bands = b->bands; a.gain = b->gain;
+    a.sf = b->sf; a.sfc = b->sfc; a.p_lo = b->p_lo; a.p_frac = b->p_frac; a.scale = b->scale;
+    a.normalize_max = b->normalize_max; a.fresh = (fresh || !state) ? 1 : 0;
+    const size_t st_bytes = (size_t)n_ch * (1 + b->n_valid) * sizeof(float);
+    if (mem == OMEGA4_MEM_HOST) {
+        int rc = b->h_spec.ensure(rows * b->T * sizeof(float)); if (rc) return rc;
+        rc = b->h_out.ensure(rows * b->n_valid * sizeof(float)); if (rc) return rc;
+        CK(cudaMemcpyAsync(b->h_spec.p, spectrum, rows * b->T * sizeof(float), cudaMemcpyHostToDevice, s));
+        a.spec = (const float*)b->h_spec.p; a.bars_out = (float*)b->h_out.p;
+        if (peak_values) { rc = b->h_peak.ensure(rows * b->n_valid * sizeof(float)); if (rc) return rc; a.peaks_out = (float*)b->h_peak.p; }
+        if (state) {
+            rc = b->h_state.ensure(st_bytes); if (rc) return rc;
+            if (!a.fresh) CK(cudaMemcpyAsync(b->h_state.p, state, st_bytes, cudaMemcpyHostToDevice, s));
+            a.state = (float*)b->h_state.p;
+        }
+    } else if (mem == OMEGA4_MEM_DEVICE) {
+        a.spec = spectrum; a.bars_out = band_values; a.peaks_out = peak_values; a.state = state;
+    } else {
+        return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
+    }
+    const size_t smem = bars_smem_bytes(b->T, b->n_valid);
+    if (smem > 200 * 1024) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel");
+    CK(cudaFuncSetAttribute(bars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bars_kernel<<<n_ch, BARS_WARPS * 32, smem, s>>>(a);
+    CK(cudaGetLastError());
+    if (mem == OMEGA4_MEM_HOST) {
+        CK(cudaMemcpyAsync(band_values, a.bars_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (peak_values) CK(cudaMemcpyAsync(peak_values, a.peaks_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (state) CK(cudaMemcpyAsync(state, a.state, st_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     return OMEGA4_OK;
 }

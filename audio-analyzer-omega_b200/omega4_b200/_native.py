@@ -34,6 +34,7 @@ EXPORTS = (
     "omega4_plan_create", "omega4_plan_destroy", "omega4_analyze", "omega4_combine",
     "omega4_meter_frames", "omega4_meter_stats", "omega4_rfft_batch", "omega4_band_map",
     "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
+    "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
 )
 
 
@@ -57,6 +58,18 @@ class PlanDesc(C.Structure):
         ("meter_hann", C.POINTER(C.c_double)),
         ("kw_coeffs", C.POINTER(C.c_double)),
         ("gate_threshold", C.c_double),
+    ]
+
+
+class BarsDesc(C.Structure):
+    _fields_ = [
+        ("spectrum_len", C.c_int), ("n_bars", C.c_int),
+        ("bands", C.POINTER(C.c_int)),
+        ("gain", C.POINTER(C.c_float)),
+        ("smooth", C.POINTER(C.c_double)),
+        ("percentile", C.c_double),
+        ("scale", C.c_float),
+        ("normalize_max", C.c_int),
     ]
 
 
@@ -106,6 +119,14 @@ def lib() -> C.CDLL:
         l.omega4_plan_launches.argtypes = [vp]
         l.omega4_plan_kernel_times.restype = ip
         l.omega4_plan_kernel_times.argtypes = [vp, vp, vp, ip]
+        l.omega4_bars_create.restype = vp
+        l.omega4_bars_create.argtypes = [C.POINTER(BarsDesc), ip]
+        l.omega4_bars_destroy.restype = None
+        l.omega4_bars_destroy.argtypes = [vp]
+        l.omega4_bars_count.restype = ip
+        l.omega4_bars_count.argtypes = [vp]
+        l.omega4_bars_run.restype = ip
+        l.omega4_bars_run.argtypes = [vp, vp, ip, vp, ip, ip, vp, ip, vp, vp]
         if l.omega4_abi_version() != ABI_VERSION:
             raise Omega4CudaError(f"{LIB_NAME} ABI {l.omega4_abi_version()} != binding ABI {ABI_VERSION}")
         _lib = l

@@ -126,6 +126,35 @@ def mel_scale_factors(frequencies: np.ndarray) -> np.ndarray:
     return np.select([f < 250, f < 500, f < 2000, f < 6000], [1.5, 1.3, 1.1, 1.0], 0.9)
 
 
+# ------------------------------------------------------------------ app-level post-processing
+def app_compensation_gains(freqs: np.ndarray, content_type: str = "instrumental",
+                           vocal_suppression: float = 0.0) -> np.ndarray:
+    """Per-bin float32 gains of ProfessionalLiveAudioAnalyzer.apply_frequency_compensation
+    (omega4_main.py:855-926): the in-place ``compensated[mask] *= g`` statements run on ones."""
+    f = np.asarray(freqs)
+    c = np.ones(len(f), dtype=np.float32)
+    if content_type == "vocal":
+        for m, g in ((f < 60, 0.15), ((f >= 60) & (f < 250), 0.2), ((f >= 250) & (f < 500), 0.6),
+                     ((f >= 500) & (f < 2000), 1.5)):
+            c[m] *= g
+    else:
+        for m, g in ((f < 60, 0.8), ((f >= 60) & (f < 250), 1.0), ((f >= 250) & (f < 500), 1.1),
+                     ((f >= 500) & (f < 2000), 0.85)):
+            c[m] *= g
+    c[(f >= 2000) & (f < 6000)] *= 1.2
+    c[(f >= 6000) & (f < 10000)] *= 0.8
+    c[f >= 10000] *= 0.3
+    if vocal_suppression > 0:
+        c[(f >= 800) & (f < 4000)] *= (1.0 - vocal_suppression * 0.5)
+    return c
+
+
+def app_smoothing_factors(bands, sample_rate: int, fft_size_base: int) -> np.ndarray:
+    """omega4_main.py:1043-1052: band start bin -> Hz -> 0.6 (< 250 Hz) / 0.75 (< 2 kHz) / 0.85."""
+    hz = np.array([s for s, _e in bands], dtype=np.float64) * sample_rate / fft_size_base
+    return np.where(hz < 250, 0.6, np.where(hz < 2000, 0.75, 0.85))
+
+
 # ------------------------------------------------------------------ meters
 def butter2_highpass(fc: float, fs: float):
     """scipy.signal.butter(2, fc/(fs/2), 'high') in closed form (bilinear transform with

@@ -136,6 +136,34 @@ int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams
                       long long n_samples, long long row_stride, int first_stream, int sample_rate,
                       long long clip_samples);
 
+/* ---- application post-processing ---------------------------- */
+/* The block of ProfessionalLiveAudioAnalyzer.process_audio_spectrum between the combined spectrum and
+ * `band_values` (omega4_main.py:992-1056): np.percentile(spectrum, 98) normalisation x 0.8,
+ * apply_frequency_compensation (:855-926, as a per-bin gain table), optional max normalisation,
+ * mel band mean -> sqrt -> clamp [0,1] over PrecomputedFrequencyMapper's band table (the loop stops
+ * at the first band reaching past the spectrum, :1012-1013), per-band exponential smoothing
+ * against the previous frame (:1041-1056).  Tables are host pointers, copied at creation. */
+typedef struct omega4_bars omega4_bars;
+typedef struct omega4_bars_desc {
+    int spectrum_len;              /* T: length of one combined spectrum (self.bars) */
+    int n_bars;                    /* entries in `bands` */
+    const int* bands;              /* [n_bars][2] (start, end) FFT-bin pairs (freq_mapper.py:83-124) */
+    const float* gain;             /* [T] frequency-compensation gains, or NULL (freq_compensation_enabled off) */
+    const double* smooth;          /* [n_bars] smoothing factor per band (:1046-1052), or NULL (smoothing off) */
+    double percentile;             /* 98 */
+    float scale;                   /* 0.8 */
+    int normalize_max;             /* normalization_enabled (:1005) */
+} omega4_bars_desc;
+omega4_bars* omega4_bars_create(const omega4_bars_desc* desc, int device);
+void omega4_bars_destroy(omega4_bars* bars);
+/* number of bars produced per frame: bands whose end <= spectrum_len, at most n_bars */
+int omega4_bars_count(const omega4_bars* bars);
+/* spectrum [n_ch][n_hops][T] -> band_values [n_ch][n_hops][count] (+ peak_values = unsmoothed, or NULL).
+ * state [n_ch][1 + count] float32 carries prev_band_values between calls (state[0] != 0: present);
+ * NULL or fresh != 0 starts every channel without a previous frame. */
+int omega4_bars_run(omega4_bars* bars, void* stream, int mem, const float* spectrum, int n_ch, int n_hops,
+                    float* state, int fresh, float* band_values, float* peak_values);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this library launched through `plan` since creation */
 long long omega4_plan_launches(const omega4_plan* plan);

@@ -425,6 +425,98 @@ def magnitude_to_db(x) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# app-level spectrum post-processing (omega4_main.py:855-926, 992-1056) -- SURVEY.md section 8f rank 1
+# --------------------------------------------------------------------------------------
+def app_compensation_gains(freqs, content_type: str = "instrumental", vocal_suppression: float = 0.0) -> np.ndarray:
+    """apply_frequency_compensation (omega4_main.py:855-926) applied to a vector of ones: the
+    per-bin float32 gain the in-place ``compensated[mask] *= g`` statements leave behind."""
+    f = np.asarray(freqs)
+    c = np.ones(len(f), dtype=np.float32)
+    if content_type == "vocal":                                   # :876-891
+        c[f < 60] *= 0.15
+        c[(f >= 60) & (f < 250)] *= 0.2
+        c[(f >= 250) & (f < 500)] *= 0.6
+        c[(f >= 500) & (f < 2000)] *= 1.5
+    else:                                                         # :892-908
+        c[f < 60] *= 0.8
+        c[(f >= 60) & (f < 250)] *= 1.0
+        c[(f >= 250) & (f < 500)] *= 1.1
+        c[(f >= 500) & (f < 2000)] *= 0.85
+    c[(f >= 2000) & (f < 6000)] *= 1.2                            # :911-912
+    c[(f >= 6000) & (f < 10000)] *= 0.8                           # :915-916
+    c[f >= 10000] *= 0.3                                          # :919-920
+    if vocal_suppression > 0:                                     # :922-925
+        c[(f >= 800) & (f < 4000)] *= (1.0 - vocal_suppression * 0.5)
+    return c
+
+
+def app_smoothing_factors(bands, sample_rate: int = SAMPLE_RATE, fft_size_base: int = FFT_SIZE_BASE) -> np.ndarray:
+    """Per-bar smoothing factor of omega4_main.py:1043-1052 (band start bin -> Hz -> 0.6 / 0.75 / 0.85)."""
+    out = np.empty(len(bands), dtype=np.float64)
+    for i, (s, _e) in enumerate(bands):
+        hz = s * sample_rate / fft_size_base
+        out[i] = 0.6 if hz < 250 else (0.75 if hz < 2000 else 0.85)
+    return out
+
+
+class OracleSpectrumPost:
+    """The block of ProfessionalLiveAudioAnalyzer.process_audio_spectrum between the combined
+    spectrum and ``band_values`` (omega4_main.py:992-1056), one frame at a time:
+    P98 normalisation x 0.8 -> frequency compensation -> optional max normalisation -> mel band
+    mean -> sqrt -> clamp [0, 1] -> per-band exponential smoothing against the previous frame.
+    ``self.freqs`` there is rfftfreq(FFT_SIZE_BASE) cut to the spectrum length (:168, :1006), and the
+    band table is the one built for FFT_SIZE_BASE/2+1 bins (:171-178) applied to the (shorter)
+    combined spectrum: the loop stops at the first band reaching past it (:1012-1013)."""
+
+    def __init__(self, bars: int = BARS_DEFAULT, sample_rate: int = SAMPLE_RATE, fft_size_base: int = FFT_SIZE_BASE,
+                 freq_compensation: bool = True, normalization: bool = False, smoothing: bool = True,
+                 content_type: str = "instrumental", vocal_suppression: float = 0.0):
+        self.bars = bars
+        self.bands = mel_band_indices(sample_rate, fft_size_base, bars)
+        self.freqs = np.fft.rfftfreq(fft_size_base, 1 / sample_rate)
+        self.freq_compensation, self.normalization, self.smoothing = freq_compensation, normalization, smoothing
+        self.content_type, self.vocal_suppression = content_type, vocal_suppression
+        self.sf = app_smoothing_factors(self.bands, sample_rate, fft_size_base)
+        self.prev = None
+
+    def n_valid(self, spectrum_len: int) -> int:
+        n = 0
+        for _s, e in self.bands:
+            if e > spectrum_len:
+                break
+            n += 1
+        return min(n, self.bars)
+
+    def process(self, spectrum) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (band_values after smoothing, peak_values = band values before smoothing)."""
+        spectrum = np.asarray(spectrum)
+        if np.max(spectrum) > 0:                                          # :992-998
+            ref = np.percentile(spectrum, 98)
+            if ref > 0:
+                spectrum = spectrum / ref * 0.8
+        if self.freq_compensation:                                        # :1001-1002
+            gains = app_compensation_gains(self.freqs[:len(spectrum)], self.content_type, self.vocal_suppression)
+            spectrum = spectrum * gains[:len(spectrum)]
+        if self.normalization and np.max(spectrum) > 0:                   # :1005-1006
+            spectrum = spectrum / np.max(spectrum)
+        vals = []
+        for s, e in self.bands:                                           # :1012-1032
+            if e > len(spectrum):
+                break
+            v = np.mean(spectrum[s:e]) if e > s else (spectrum[s] if s < len(spectrum) else 0)
+            if v > 0:
+                v = max(0, min(1, np.sqrt(v)))
+            vals.append(v)
+        band = np.array(vals[:self.bars])
+        peak = band.copy()
+        if self.smoothing and self.prev is not None:                      # :1041-1054
+            for i in range(len(band)):
+                band[i] = self.prev[i] * self.sf[i] + band[i] * (1 - self.sf[i])
+        self.prev = band.copy()
+        return band, peak
+
+
+# --------------------------------------------------------------------------------------
 # professional meters (omega4/panels/professional_meters.py)
 # --------------------------------------------------------------------------------------
 def butter2_highpass(fc: float, fs: float):

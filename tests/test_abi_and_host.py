@@ -216,3 +216,13 @@ def test_plan_helpers_and_synth():
     assert sum(c for _, c in all_blocks(8192, 8)) == 8192 and stream_block(8192, 8, 7) == (7168, 1024)
     with pytest.raises(ValueError):
         stream_block(4, 2, 2)
+
+
+def test_app_post_tables_match_oracle():
+    from omega4_b200 import tables
+    from oracle import oracle_np as O
+    f = np.fft.rfftfreq(2048, 1 / 48000)[:512]
+    for ct, vs in (("instrumental", 0.0), ("vocal", 0.5), ("bass_heavy", 0.25)):
+        assert np.array_equal(tables.app_compensation_gains(f, ct, vs), O.app_compensation_gains(f, ct, vs))
+    bands = tables.mel_band_indices(48000, 2048, 512)
+    assert np.array_equal(tables.app_smoothing_factors(bands, 48000, 2048), O.app_smoothing_factors(bands, 48000, 2048))

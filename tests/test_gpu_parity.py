@@ -240,6 +240,66 @@ def test_blockdft_96k_default_and_window_variants(golden):
     p.close()
 
 
+# ------------------------------------------------------------------ section 8f rank 1: app post-processing
+TOL_BAR = 1e-5     # band_values live in [0, 1]; 0.01 dB on the spectrum is 5.8e-4 relative on a sqrt'd bar
+
+
+def test_app_post_processing_golden_and_state():
+    """omega4_bars_run vs omega4_main.py:992-1056 executed unmodified (tests/golden/app_post.npz)."""
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    g = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "app_post.npz"))
+    comb = g["combined"]
+    variants = {"default": {}, "normalized": {"normalization_enabled": True},
+                "vocal": {"current_content_type": "vocal", "vocal_suppression": 0.5},
+                "plain": {"freq_compensation_enabled": False, "smoothing_enabled": False}}
+    for name, attrs in variants.items():
+        post = SpectrumPostProcessor(512)
+        for k, v in attrs.items():
+            setattr(post, k, v)
+        band, peak = post.process_host(comb[None], want_peaks=True)
+        assert band.shape == (1, len(comb), 437)
+        assert np.abs(peak[0] - g["peak_" + name]).max() <= TOL_BAR, name
+        assert np.abs(band[0] - g["band_" + name]).max() <= TOL_BAR, name
+        post.close()
+    # frame-at-a-time (the application's call pattern, prev_band_values carried on the object)
+    post = SpectrumPostProcessor(512)
+    for k in range(20):
+        b, p = post.process(comb[k])
+        assert np.abs(b - g["band_default"][k]).max() <= TOL_BAR and np.abs(p - g["peak_default"][k]).max() <= TOL_BAR
+    assert np.array_equal(post.prev_band_values, b)
+    # tiles with carried state == one shot; channels independent
+    one = post.process_host(np.stack([comb, comb[::-1]]))
+    state = np.zeros((2, 1 + post.n_valid), np.float32)
+    parts = [post.process_host(np.stack([comb, comb[::-1]])[:, s:s + 13], state=state) for s in range(0, len(comb), 13)]
+    assert np.array_equal(np.concatenate(parts, axis=1), one)
+    assert np.abs(one[0] - g["band_default"]).max() <= TOL_BAR
+    post.close()
+
+
+def test_app_post_processing_resident_batch_against_oracle(plan):
+    """Device-resident chain: analyze -> combined -> band_values, against the numpy oracle."""
+    import torch
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    from omega4_b200.batch.driver import analyze_resident
+    from omega4_b200.batch.synth import synth_streams
+    n_hops = 70
+    x = synth_streams(2, 2, n_hops * HOP).reshape(4, -1)
+    comb = torch.empty((4, n_hops, 512), device="cuda")
+    analyze_resident(plan, torch.from_numpy(x).cuda(), combined=comb)
+    post = SpectrumPostProcessor(512)
+    post._ensure()
+    bars = torch.empty((4, n_hops, post.n_valid), device="cuda")
+    post.process_device(comb, bars)
+    torch.cuda.synchronize()
+    got = bars.cpu().numpy()
+    c = comb.cpu().numpy()
+    for ch in (0, 3):
+        ref = O.OracleSpectrumPost(512)
+        want = np.stack([ref.process(row)[0] for row in c[ch]])
+        assert np.abs(got[ch] - want).max() <= TOL_BAR
+    post.close()
+
+
 # ------------------------------------------------------------------ meters
 def test_meters_stream_golden(plan, golden):
     g = golden("meters_stream.npz")

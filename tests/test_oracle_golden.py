@@ -287,3 +287,23 @@ def test_ref_port_matches_oracle(golden):
     np.testing.assert_allclose(meters[3:], g["meters"][:57], rtol=0, atol=1e-8)
     r = ref_port.time_cpu_path(2, 2, 0.25, processes=2)
     assert r["value"] > 0 and r["cores"] == 2
+
+
+# ---------------------------------------------------------------- section 8f rank 1: app post-processing
+@pytest.mark.parametrize("variant,kw", [
+    ("default", {}),
+    ("normalized", {"normalization": True}),
+    ("vocal", {"content_type": "vocal", "vocal_suppression": 0.5}),
+    ("plain", {"freq_compensation": False, "smoothing": False}),
+])
+def test_app_post_processing_matches_reference_block(golden, variant, kw):
+    """oracle OracleSpectrumPost vs omega4_main.py:992-1056 executed unmodified (gen_golden_next.py)."""
+    g = golden("app_post.npz")
+    post = O.OracleSpectrumPost(512, **kw)
+    assert np.array_equal(np.array(post.bands, dtype=np.int32), g["bands"])
+    assert post.n_valid(512) == g["band_" + variant].shape[1] == 437
+    for k, row in enumerate(g["combined"]):
+        band, peak = post.process(row)
+        np.testing.assert_allclose(peak, g["peak_" + variant][k], rtol=0, atol=1.2e-7)
+        np.testing.assert_allclose(band, g["band_" + variant][k], rtol=0, atol=2.4e-7)
+    assert float(g["band_default"].max()) == 1.0 and float(g["band_default"].min()) == 0.0
