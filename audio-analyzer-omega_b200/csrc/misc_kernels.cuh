@@ -77,6 +77,28 @@ __global__ void band_map_kernel(const float* __restrict__ spec, int n_rows, int 
 // from the (stream, channel) hash of omega4_b200/batch/synth.py, plus white counter-hash noise of
 // RMS 0.1 (the numpy generator shapes its noise pink; spectral colour is irrelevant to throughput).
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Wire format of the capture side: interleaved little-endian int16 frames ->
+// planar float32 rows,  x = int16 / 32768  (omega4/audio/capture.py:571-574; exact in float32).
+// Stream g, frame i, channel c  ->  out[(g*il + c) * out_stride + i]
+// ---------------------------------------------------------------------------------------------
+__global__ void s16_deinterleave_kernel(const int16_t* __restrict__ in, long long stream_stride, int il,
+                                        long long n_frames, float* __restrict__ out, long long out_stride) {
+    const int g = blockIdx.y;
+    const int16_t* src = in + (long long)g * stream_stride;
+    const long long total = n_frames * il;
+    const long long base = (long long)blockIdx.x * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long e = base + threadIdx.x + 256 * k;          // element index in the interleaved stream
+        if (e < total) {
+            const long long i = e / il;
+            const int c = (int)(e - i * il);
+            out[((long long)g * il + c) * out_stride + i] = (float)src[e] * (1.0f / 32768.0f);
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     return h;

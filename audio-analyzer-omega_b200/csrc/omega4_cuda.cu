@@ -171,6 +171,17 @@ static int launch_stats(const StatsArgs& a, cudaStream_t s) {
     return OMEGA4_OK;
 }
 
+static int launch_s16_convert(const int16_t* in, long long stream_stride, int il, int n_streams, long long n_frames,
+                              float* out, long long out_stride, cudaStream_t s) {
+    if (n_streams <= 0 || n_frames <= 0) return OMEGA4_OK;
+    if (n_streams > 65535) return fail(OMEGA4_ERR_INVALID, "too many streams for one int16 conversion launch (max 65535)");
+    const long long per_stream = n_frames * il;
+    dim3 grid((unsigned)((per_stream + 1023) / 1024), (unsigned)n_streams);
+    s16_deinterleave_kernel<<<grid, 256, 0, s>>>(in, stream_stride, il, n_frames, out, out_stride);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // K-weighting scan tables
 // ------------------------------------------------------------------------------------------
@@ -271,13 +282,13 @@ struct omega4_plan {
     int sp_n = 0, sp_bn = 0;      // sparse resolutions, padded column count of their shared GEMM
     SparseRes sp[OMEGA4_MAX_RES];
     float* sp_E = nullptr;        // [hop][sp_bn]
-    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q;
+    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32;
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
     // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
     // that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
     struct Slot {
         cudaStream_t s = nullptr;
-        DevBuf in, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
+        DevBuf in, in16, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
     };
     static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
@@ -513,14 +524,14 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     }
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
     cudaFree(p->hann64); cudaFree(p->hann32);
-    p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release();
+    p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
     for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(p->sp[i].T); cudaFree(p->sp[i].kw); cudaFree(p->sp[i].tb_pos); }
     cudaFree(p->sp_E);
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
     for (auto& sl : p->slots) {
         sl.in.release(); sl.comb.release(); sl.met.release(); sl.lufs.release(); sl.tp.release(); sl.state.release();
-        sl.q.release();
+        sl.q.release(); sl.in16.release();
         for (auto& m : sl.mag) m.release();
         if (sl.s) cudaStreamDestroy(sl.s);
     }
@@ -765,17 +776,36 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     return OMEGA4_OK;
 }
 
-extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float* samples, long long ch_stride,
-                              int n_ch, int n_hops, int hist_samples, float* combined, float* const* magnitudes,
-                              float* meters, double* lufs_inst, double* tp_db, double* meter_state, int flags) {
+// s16 != nullptr: the input is interleaved little-endian int16 (capture.py:571-574), `il` channels per
+// stream, stream g starting at s16 + g*ch_stride (int16 units, pointing at the first NEW frame;
+// hist_samples frames precede it); n_ch = streams * il planar channels come out of the conversion.
+static int analyze_any(omega4_plan* p, void* stream, int mem, const float* samples, const int16_t* s16, int il,
+                       long long ch_stride, int n_ch, int n_hops, int hist_samples, float* combined,
+                       float* const* magnitudes, float* meters, double* lufs_inst, double* tp_db,
+                       double* meter_state, int flags) {
     if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
-    if (!samples || n_ch < 0 || n_hops < 0 || hist_samples < 0) return fail(OMEGA4_ERR_INVALID, "bad samples / sizes");
+    if ((!samples && !s16) || n_ch < 0 || n_hops < 0 || hist_samples < 0) return fail(OMEGA4_ERR_INVALID, "bad samples / sizes");
+    if (s16 && (il < 1 || il > 64 || n_ch % il != 0)) return fail(OMEGA4_ERR_INVALID, "bad interleave");
     if (n_ch == 0 || n_hops == 0) return OMEGA4_OK;
     CK(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if (mem == OMEGA4_MEM_DEVICE)
+    if (mem == OMEGA4_MEM_DEVICE) {
+        if (s16) {
+            const long long hist_al = ((long long)hist_samples + 3) / 4 * 4;
+            const long long len = (long long)hist_samples + (long long)n_hops * p->hop;
+            const long long dstride = (hist_al + (long long)n_hops * p->hop + 3) / 4 * 4;
+            int rc = p->scratch_f32.ensure((size_t)n_ch * dstride * sizeof(float)); if (rc) return rc;
+            float* d_in = (float*)p->scratch_f32.p;
+            p->launches++;
+            rc = launch_s16_convert(s16 - (long long)hist_samples * il, ch_stride, il, n_ch / il, len,
+                                    d_in + (hist_al - hist_samples), dstride, s);
+            if (rc) return rc;
+            return analyze_device(p, s, d_in + hist_al, dstride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
+                                  lufs_inst, tp_db, meter_state, flags, &p->scratch_q);
+        }
         return analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
                               lufs_inst, tp_db, meter_state, flags, &p->scratch_q);
+    }
     if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
 
     // ---- host buffers: channel chunks pipelined over private streams (H2D | kernels | D2H overlap)
@@ -793,9 +823,11 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
         want_mag[r] = (magnitudes && magnitudes[r]) || (combined && !p->disjoint);
         if (want_mag[r]) per_ch += (size_t)n_hops * p->res[r].bins * sizeof(float);
     }
+    if (s16) per_ch += (size_t)(hist + new_len) * sizeof(int16_t);
     int chunk = (int)(p->host_chunk_bytes / per_ch);
     if (chunk < 1) chunk = 1;
     if (chunk > n_ch) chunk = n_ch;
+    if (s16) { chunk = chunk / il * il; if (chunk < il) chunk = il; }     // whole streams per chunk
     const bool want_series = meters || lufs_inst || tp_db;
     int idx = 0;
     for (int c0 = 0; c0 < n_ch; c0 += chunk, ++idx) {
@@ -805,9 +837,22 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
         const size_t rows = (size_t)nc * n_hops;
         int rc = sl.in.ensure((size_t)nc * dstride * sizeof(float)); if (rc) return rc;
         float* d_in = (float*)sl.in.p;
-        CK(cudaMemcpy2DAsync(d_in + (hist_al - hist), dstride * sizeof(float),
-                             samples + (long long)c0 * ch_stride - hist, ch_stride * sizeof(float),
-                             (size_t)(hist + new_len) * sizeof(float), nc, cudaMemcpyHostToDevice, sl.s));
+        if (s16) {
+            const int ns = nc / il;                                   // streams in this chunk
+            const size_t row16 = (size_t)(hist + new_len) * il;       // int16 per stream
+            rc = sl.in16.ensure((size_t)ns * row16 * sizeof(int16_t)); if (rc) return rc;
+            CK(cudaMemcpy2DAsync(sl.in16.p, row16 * sizeof(int16_t),
+                                 s16 + (long long)(c0 / il) * ch_stride - hist * il, ch_stride * sizeof(int16_t),
+                                 row16 * sizeof(int16_t), ns, cudaMemcpyHostToDevice, sl.s));
+            p->launches++;
+            rc = launch_s16_convert((const int16_t*)sl.in16.p, (long long)row16, il, ns, hist + new_len,
+                                    d_in + (hist_al - hist), dstride, sl.s);
+            if (rc) return rc;
+        } else {
+            CK(cudaMemcpy2DAsync(d_in + (hist_al - hist), dstride * sizeof(float),
+                                 samples + (long long)c0 * ch_stride - hist, ch_stride * sizeof(float),
+                                 (size_t)(hist + new_len) * sizeof(float), nc, cudaMemcpyHostToDevice, sl.s));
+        }
         float* d_comb = nullptr; float* d_met = nullptr; double* d_state = nullptr;
         double* d_lufs = nullptr; double* d_tp = nullptr;
         float* d_mag[OMEGA4_MAX_RES] = {nullptr};
@@ -851,6 +896,24 @@ extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float
     for (auto& sl : p->slots)
         if (sl.s) CK(cudaStreamSynchronize(sl.s));
     return OMEGA4_OK;
+}
+
+extern "C" int omega4_analyze(omega4_plan* p, void* stream, int mem, const float* samples, long long ch_stride,
+                              int n_ch, int n_hops, int hist_samples, float* combined, float* const* magnitudes,
+                              float* meters, double* lufs_inst, double* tp_db, double* meter_state, int flags) {
+    if (!samples) return fail(OMEGA4_ERR_INVALID, "bad samples / sizes");
+    return analyze_any(p, stream, mem, samples, nullptr, 1, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes,
+                       meters, lufs_inst, tp_db, meter_state, flags);
+}
+
+extern "C" int omega4_analyze_s16(omega4_plan* p, void* stream, int mem, const int16_t* frames, long long stream_stride,
+                                  int n_streams, int n_interleaved, int n_hops, int hist_frames, float* combined,
+                                  float* const* magnitudes, float* meters, double* lufs_inst, double* tp_db,
+                                  double* meter_state, int flags) {
+    if (!frames || n_streams < 0 || n_interleaved < 1) return fail(OMEGA4_ERR_INVALID, "bad frames / sizes");
+    if (mem == OMEGA4_MEM_DEVICE && ((uintptr_t)frames & 1)) return fail(OMEGA4_ERR_INVALID, "frames must be 2-byte aligned");
+    return analyze_any(p, stream, mem, nullptr, frames, n_interleaved, stream_stride, n_streams * n_interleaved, n_hops,
+                       hist_frames, combined, magnitudes, meters, lufs_inst, tp_db, meter_state, flags);
 }
 
 // ------------------------------------------------------------------------------------------

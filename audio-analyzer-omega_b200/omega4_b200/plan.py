@@ -210,6 +210,45 @@ class AnalysisPlan:
                                     N.ptr(meters), N.ptr(lufs_inst), N.ptr(tp_db), N.ptr(meter_state), flags)
         N.check(rc, "omega4_analyze")
 
+    # ------------------------------------------------------------------ int16 wire format
+    def analyze_s16_host(self, frames: np.ndarray, hist_frames: int = 0, want_combined: bool = True,
+                         want_meters: bool = True, want_series: bool = False, flags: int = 0) -> Dict[str, object]:
+        """Interleaved int16 frames as the capture side delivers them ("s16le", x = int16/32768,
+        omega4/audio/capture.py:571-574): ``frames`` int16 [n_streams, hist_frames + n_hops*hop, C]
+        (or [n_streams, n] for mono).  Outputs are indexed by planar channel stream*C + c."""
+        f = np.ascontiguousarray(frames, dtype=np.int16)
+        if f.ndim == 2:
+            f = f[:, :, None]
+        n_streams, total, il = f.shape
+        n_hops = (total - hist_frames) // self.hop
+        out: Dict[str, object] = {"n_hops": n_hops}
+        if n_streams == 0 or n_hops <= 0:
+            return out
+        n_ch = n_streams * il
+        comb = np.empty((n_ch, n_hops, self.target_bins), np.float32) if want_combined else None
+        met = np.empty((n_ch, n_hops, N.N_METERS), np.float32) if want_meters else None
+        li = np.empty((n_ch, n_hops), np.float64) if want_series else None
+        tp = np.empty((n_ch, n_hops), np.float64) if want_series else None
+        base = f.ctypes.data + hist_frames * il * 2
+        rc = N.lib().omega4_analyze_s16(self.handle, None, N.MEM_HOST, base, f.strides[0] // 2, n_streams, il, n_hops,
+                                        hist_frames, N.ptr(comb), None, N.ptr(met), N.ptr(li), N.ptr(tp), None, flags)
+        N.check(rc, "omega4_analyze_s16")
+        out.update(combined=comb, meters=met, lufs_inst=li, tp_db=tp)
+        return out
+
+    def analyze_s16_device(self, frames, n_hops: int, n_interleaved: int, hist_frames: int = 0, combined=None,
+                           meters=None, meter_state=None, flags: int = 0, stream=None):
+        """Device tensor int16 [n_streams, >= (hist_frames + n_hops*hop) * C] (interleaved)."""
+        import torch
+        assert frames.is_cuda and frames.dtype == torch.int16 and frames.stride(-1) == 1
+        if stream is None:
+            stream = torch.cuda.current_stream(frames.device).cuda_stream
+        base = frames.data_ptr() + hist_frames * n_interleaved * 2
+        rc = N.lib().omega4_analyze_s16(self.handle, stream, N.MEM_DEVICE, base, frames.stride(0), frames.shape[0],
+                                        n_interleaved, n_hops, hist_frames, N.ptr(combined), None, N.ptr(meters),
+                                        None, None, N.ptr(meter_state), flags)
+        N.check(rc, "omega4_analyze_s16")
+
     # ------------------------------------------------------------------ pieces used by the shims
     def combine_host(self, magnitudes: Sequence[Optional[np.ndarray]], n_rows: int = 1) -> np.ndarray:
         mags = [None if m is None else np.ascontiguousarray(m, dtype=np.float32).reshape(n_rows, -1) for m in magnitudes]

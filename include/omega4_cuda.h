@@ -100,6 +100,18 @@ int omega4_analyze(omega4_plan* plan, void* stream, int mem,
                    float* combined, float* const* magnitudes, float* meters,
                    double* lufs_inst, double* tp_db, double* meter_state, int flags);
 
+/* Same path fed with the capture side's wire format: interleaved
+ * little-endian int16 frames, x = int16 / 32768 as AudioCaptureManager._capture_loop decodes "s16le"
+ * (omega4/audio/capture.py:571-574).  Stream g starts at frames + g*stream_stride (int16 units, first
+ * NEW frame; hist_frames frames precede it); n_interleaved channels per frame (1 = the capture's mono
+ * chunks, 2 / 8 = stereo / 7.1 files).  Outputs are indexed by planar channel g*n_interleaved + c,
+ * n_ch = n_streams*n_interleaved, exactly as omega4_analyze's.  Halves the host->device bytes. */
+int omega4_analyze_s16(omega4_plan* plan, void* stream, int mem,
+                       const short* frames, long long stream_stride, int n_streams, int n_interleaved,
+                       int n_hops, int hist_frames,
+                       float* combined, float* const* magnitudes, float* meters,
+                       double* lufs_inst, double* tp_db, double* meter_state, int flags);
+
 /* combine_results_optimized (multi_resolution_fft.py:335-408) on caller-supplied magnitudes:
  * magnitudes[r] = [n_rows][N_r/2+1] or NULL when resolution r is absent from `results`. */
 int omega4_combine(omega4_plan* plan, void* stream, int mem,

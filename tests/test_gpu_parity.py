@@ -300,6 +300,40 @@ def test_app_post_processing_resident_batch_against_oracle(plan):
     post.close()
 
 
+# ------------------------------------------------------------------ section 8f rank 4: s16le wire format
+def test_s16_interleaved_input_is_bit_identical_to_float_path(plan):
+    """capture.py:571-574 decodes s16le as int16.astype(float32) / 32768 -- exact in float32, so the
+    int16 entry point must reproduce the float32 entry point bit for bit (mono, stereo, 7.1)."""
+    import torch
+    rng = np.random.default_rng(21)
+    n_hops = 40
+    for il, n_streams in ((1, 3), (2, 2), (8, 1)):
+        pcm = rng.integers(-32768, 32768, size=(n_streams, n_hops * HOP, il), dtype=np.int16)
+        pcm[0, 5 * HOP:9 * HOP] = 0                                       # digital silence
+        planar = (pcm.astype(np.float32) / 32768.0).transpose(0, 2, 1).reshape(n_streams * il, -1)
+        ref = plan.analyze_host(planar)
+        got = plan.analyze_s16_host(pcm)
+        assert np.array_equal(got["combined"], ref["combined"]) and np.array_equal(got["meters"], ref["meters"])
+        # device-resident int16, with carried history: second half of the clip as a tile
+        d = torch.from_numpy(pcm.reshape(n_streams, -1)).cuda()
+        comb = torch.empty((n_streams * il, n_hops, 512), device="cuda")
+        met = torch.empty((n_streams * il, n_hops, 5), device="cuda")
+        plan.analyze_s16_device(d, n_hops, il, combined=comb, meters=met)
+        torch.cuda.synchronize()
+        assert np.array_equal(comb.cpu().numpy(), ref["combined"]) and np.array_equal(met.cpu().numpy(), ref["meters"])
+        h = 20
+        tail = plan.analyze_s16_host(pcm, hist_frames=h * HOP, want_meters=False)
+        assert np.array_equal(tail["combined"], plan.analyze_host(planar, hist_samples=h * HOP, want_meters=False)["combined"])
+        assert np.array_equal(tail["combined"], ref["combined"][:, h:])      # 20 hops of history cover every window
+
+
+def test_s16_decode_matches_capture_formula():
+    rng = np.random.default_rng(2)
+    pcm = rng.integers(-32768, 32768, size=4096, dtype=np.int16)
+    want = np.frombuffer(pcm.tobytes(), dtype=np.int16).astype(np.float32) / 32768.0      # capture.py:574
+    assert np.array_equal(want, pcm.astype(np.float32) * np.float32(1.0 / 32768.0))
+
+
 # ------------------------------------------------------------------ meters
 def test_meters_stream_golden(plan, golden):
     g = golden("meters_stream.npz")
