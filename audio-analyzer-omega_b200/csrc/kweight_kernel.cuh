@@ -45,7 +45,10 @@ struct KwBiquad {
     double b0, b1, b2, a1, a2;
     double yi0, yi1;                // (y[-1], y[-2]) per unit x0, equivalent to scipy's lfilter_zi state
     double phi[5][4];               // (C^65)^(2^j), row major [[p00,p01],[p10,p11]], C = [[-a1,-a2],[1,0]]
-    double cinv[4];                 // C^-14
+    double cinv_f[4];               // C^-(9 - pad): forward start moved back over the unused leading slots
+    double cinv_b[4];               // C^-(14 + 9 - pad): backward start moved back over the trailing slack
+    int pad;                        // filtfilt padlen = 3 * max(len(a), len(b)): 9 (biquad) or 6 (first order)
+    int _align;
     double c16[4], c17[4];          // C^16, C^17: transitions over one sub-chunk
     double g[KW_SUBMAX][2];         // g[i] = first row of C^(i+1)  (homogeneous output response)
 };
@@ -63,7 +66,15 @@ struct KweightArgs {
     const double* hann;             // [W] float64 Hann (hop mode) or nullptr (frames already windowed)
     double* lufs_out;               // [n_ch][n_frames] instantaneous LUFS
     double* weighted_out;           // [n_ch][n_frames][W] K-weighted frame or nullptr
-    KwBiquad f[2];                  // 0: 38 Hz high-pass, 1: 1500 Hz "shelf" high-pass
+    // weighting program (professional_meters.py:129-229): n_sec zero-phase sections applied in cascade.
+    //   K: 2 sections, blend = 1: out = f0 + 0.3 (f1 - f0), f1 = section 1 applied to f0   (:137-151)
+    //   A: 4 sections, gain 2.5 (:166-190);  C: 2 sections (:205-216);  Z: 0 sections, no gate (:228-229)
+    int n_sec;
+    int blend;
+    int rms_gate;
+    int _align;
+    double gain;
+    KwBiquad f[4];
 };
 
 __device__ __forceinline__ double2 mat2_apply(const double* m, double2 s) {
@@ -75,14 +86,22 @@ template <bool BACKWARD>
 __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, int lane) {
     // scan position of this lane: 0 is processed first
     const int pos = BACKWARD ? 31 - lane : lane;
-    // the sample whose value scales the steady-state initial condition
-    double x0 = BACKWARD ? __shfl_sync(0xffffffffu, r[KW_LAST], 31) : __shfl_sync(0xffffffffu, r[0], 0);
+    // the sample whose value scales the steady-state initial condition: first / last sample of the
+    // padded sequence, which starts 9 - pad slots into lane 0 and ends 9 - pad slots before KW_LAST
+    const bool short_pad = c.pad < KW_PAD;                           // pad 6: three unused slots at either end
+    constexpr int SH = KW_PAD - 6;
+    double x0 = BACKWARD ? __shfl_sync(0xffffffffu, short_pad ? r[KW_LAST - SH] : r[KW_LAST], 31)
+                         : __shfl_sync(0xffffffffu, short_pad ? r[SH] : r[0], 0);
     if (BACKWARD && lane == 31) {
 #pragma unroll
         for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = 0.0;
+        if (short_pad) {
+#pragma unroll
+            for (int i = KW_LAST - SH + 1; i <= KW_LAST; ++i) r[i] = 0.0;
+        }
     }
     double2 s_init = make_double2(c.yi0 * x0, c.yi1 * x0);
-    if (BACKWARD) s_init = mat2_apply(c.cinv, s_init);
+    s_init = mat2_apply(BACKWARD ? c.cinv_b : c.cinv_f, s_init);
 
     // sub-chunk m (processing order) = index range j: forward j = m, backward j = 3 - m
     // length of sub-chunk m in processing order: forward 17,16,16,16 ; backward 16,16,16,17
@@ -171,15 +190,15 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
 
 // odd reflection padding of the frame held at ext positions [9, 2057): lane 0 owns ext[0..9),
 // lane 31 owns ext[2057..2066) at local 42..50.
-__device__ __forceinline__ void kw_odd_pad(double (&r)[KW_L], int lane) {
+__device__ __forceinline__ void kw_odd_pad(double (&r)[KW_L], int lane, int pad) {
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[j] = 2.0 * r[KW_PAD] - r[2 * KW_PAD - j];
+        for (int j = 0; j < KW_PAD; ++j) r[j] = (j >= KW_PAD - pad) ? 2.0 * r[KW_PAD] - r[2 * KW_PAD - j] : 0.0;
     }
     if (lane == 31) {
         constexpr int E = KW_LAST - KW_PAD;     // 41: local index of the frame's last sample
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[E + 1 + j] = 2.0 * r[E] - r[E - 1 - j];
+        for (int j = 0; j < KW_PAD; ++j) r[E + 1 + j] = (j < pad) ? 2.0 * r[E] - r[E - 1 - j] : 0.0;
     }
 }
 
@@ -268,7 +287,7 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
-        const bool gated = sqrt(sumsq / (double)KW_W) < 1e-6;          // professional_meters.py:132-134
+        const bool gated = a.rms_gate && sqrt(sumsq / (double)KW_W) < 1e-6;   // professional_meters.py:132-134
 
         double ms = 0.0;
         if (!gated) {                                                  // warp-uniform
@@ -276,12 +295,12 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
             // the two filtfilt calls share one code body (loop not unrolled: halves the instruction
             // footprint -- ncu showed 14 % instruction-fetch stalls with both inlined)
 #pragma unroll 1
-            for (int fi = 0; fi < 2; ++fi) {
-                kw_odd_pad(r, lane);
+            for (int fi = 0; fi < a.n_sec; ++fi) {
+                kw_odd_pad(r, lane, a.f[fi].pad);
                 kw_pass<false>(r, a.f[fi], lane);
                 kw_pass<true>(r, a.f[fi], lane);
                 kw_zero_pads(r, lane);
-                if (fi == 0) {
+                if (fi == 0 && a.blend) {
                     // stash f (first filtfilt output) as fp32 with zeros at the pad positions;
                     // the 65-word lane stride is bank-conflict free
 #pragma unroll
@@ -291,8 +310,13 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
             double acc = 0.0;
 #pragma unroll
             for (int i = 0; i < KW_L; ++i) {
-                const double fv = (double)fl[i];
-                const double w = fma(r[i] - fv, 0.3, fv);              // f + (s - f) * 0.3 ; 0 at the pads
+                double w;
+                if (a.blend) {
+                    const double fv = (double)fl[i];
+                    w = fma(r[i] - fv, 0.3, fv);                       // f + (s - f) * 0.3 ; 0 at the pads
+                } else {
+                    w = r[i] * a.gain;                                 // cascade (A: x 2.5, C / Z: x 1)
+                }
                 acc = fma(w, w, acc);
                 if (WEIGHTED) r[i] = w;
             }

@@ -191,39 +191,57 @@ static void mat2_mul(const double* a, const double* b, double* c) {
     memcpy(c, r, sizeof r);
 }
 
-static void build_biquad(const double* b, const double* a, KwBiquad* q) {
+// b, a: order + 1 coefficients (order 1 or 2).  Everything the scan needs is derived here in float64.
+static void build_biquad(const double* b, const double* a, int order, KwBiquad* q) {
+    memset(q, 0, sizeof *q);
     const double a0 = a[0];
-    q->b0 = b[0] / a0; q->b1 = b[1] / a0; q->b2 = b[2] / a0;
-    q->a1 = a[1] / a0; q->a2 = a[2] / a0;
-    // lfilter_zi: (I - companion(a)^T) zi = b[1:] - a[1:] b[0]
-    double zi0, zi1;
-    {
+    q->b0 = b[0] / a0; q->b1 = b[1] / a0; q->b2 = order >= 2 ? b[2] / a0 : 0.0;
+    q->a1 = a[1] / a0; q->a2 = order >= 2 ? a[2] / a0 : 0.0;
+    q->pad = 3 * (order + 1);                                // scipy filtfilt default padlen
+    if (order >= 2) {
+        // lfilter_zi: (I - companion(a)^T) zi = b[1:] - a[1:] b[0]
+        double zi0, zi1;
         const double m00 = 1.0 + q->a1, m01 = -1.0, m10 = q->a2, m11 = 1.0;
         const double r0 = q->b1 - q->a1 * q->b0, r1 = q->b2 - q->a2 * q->b0;
         const double det = m00 * m11 - m01 * m10;
         zi0 = (r0 * m11 - m01 * r1) / det;
         zi1 = (m00 * r1 - m10 * r0) / det;
+        // direct form I initial outputs equivalent to the transposed-form-II state (zi0, zi1) with
+        // x[-1] = x[-2] = 0:  -a1 y[-1] - a2 y[-2] = zi0,  -a2 y[-1] = zi1
+        q->yi0 = -zi1 / q->a2;
+        q->yi1 = (-zi0 + q->a1 * zi1 / q->a2) / q->a2;
+    } else {
+        // first order: zi = (b1 - a1 b0) / (1 + a1);  -a1 y[-1] = zi
+        const double zi0 = (q->b1 - q->a1 * q->b0) / (1.0 + q->a1);
+        q->yi0 = -zi0 / q->a1;
+        q->yi1 = 0.0;
     }
-    // direct form I initial outputs equivalent to the transposed-form-II state (zi0, zi1) with
-    // x[-1] = x[-2] = 0:  -a1 y[-1] - a2 y[-2] = zi0,  -a2 y[-1] = zi1
-    q->yi0 = -zi1 / q->a2;
-    q->yi1 = (-zi0 + q->a1 * zi1 / q->a2) / q->a2;
     // companion matrix of the output recursion: (y[n], y[n-1]) = C (y[n-1], y[n-2])
     const double Cm[4] = {-q->a1, -q->a2, 1.0, 0.0};
     double P[4] = {Cm[0], Cm[1], Cm[2], Cm[3]};       // C^(i+1)
-    double C14[4] = {1, 0, 0, 1};
     for (int i = 0; i < KW_L; ++i) {
         if (i < KW_SUBMAX) { q->g[i][0] = P[0]; q->g[i][1] = P[1]; }
-        if (i + 1 == KW_SLACK) memcpy(C14, P, sizeof P);
         if (i + 1 == 16) memcpy(q->c16, P, sizeof P);
         if (i + 1 == 17) memcpy(q->c17, P, sizeof P);
         if (i + 1 < KW_L) mat2_mul(Cm, P, P);
     }
     memcpy(q->phi[0], P, sizeof P);              // C^65
     for (int j = 1; j < 5; ++j) mat2_mul(q->phi[j - 1], q->phi[j - 1], q->phi[j]);
-    const double det = C14[0] * C14[3] - C14[1] * C14[2];
-    q->cinv[0] = C14[3] / det; q->cinv[1] = -C14[1] / det;
-    q->cinv[2] = -C14[2] / det; q->cinv[3] = C14[0] / det;
+    // C^-k for the two virtual start offsets
+    auto inv_pow = [&](int k, double* out) {
+        if (k == 0) { out[0] = 1; out[1] = 0; out[2] = 0; out[3] = 1; return; }
+        if (order >= 2) {
+            const double det1 = Cm[0] * Cm[3] - Cm[1] * Cm[2];           // = a2
+            const double Ci[4] = {Cm[3] / det1, -Cm[1] / det1, -Cm[2] / det1, Cm[0] / det1};
+            double R[4] = {Ci[0], Ci[1], Ci[2], Ci[3]};
+            for (int i = 1; i < k; ++i) mat2_mul(Ci, R, R);
+            memcpy(out, R, sizeof R);
+        } else {                                                       // singular companion: scalar recursion
+            out[0] = pow(-q->a1, -(double)k); out[1] = 0; out[2] = 0; out[3] = 0;
+        }
+    };
+    inv_pow(KW_PAD - q->pad, q->cinv_f);
+    inv_pow(KW_SLACK + KW_PAD - q->pad, q->cinv_b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -277,7 +295,10 @@ struct omega4_plan {
     int* csr_ptr = nullptr; int* csr_res = nullptr; int* csr_lo = nullptr; float* csr_frac = nullptr;
     double* hann64 = nullptr;
     float* hann32 = nullptr;
-    KwBiquad kw[2];
+    KwBiquad kw_default[2];       // the K-weighting pair of the plan descriptor
+    KwBiquad kw[4];               // active weighting program (omega4_plan_set_weighting)
+    int kw_nsec = 2, kw_blend = 1, kw_gate = 1;
+    double kw_gain = 1.0;
     Twiddles tw_meter;
     int sp_n = 0, sp_bn = 0;      // sparse resolutions, padded column count of their shared GEMM
     SparseRes sp[OMEGA4_MAX_RES];
@@ -301,6 +322,16 @@ struct omega4_plan {
     std::vector<KernelTime> times;
     size_t n_times = 0;
 };
+
+static void set_weighting_k(omega4_plan* p) {
+    p->kw[0] = p->kw_default[0]; p->kw[1] = p->kw_default[1];
+    p->kw_nsec = 2; p->kw_blend = 1; p->kw_gate = 1; p->kw_gain = 1.0;
+}
+
+static void fill_weighting(const omega4_plan* p, KweightArgs* k) {
+    k->n_sec = p->kw_nsec; k->blend = p->kw_blend; k->rms_gate = p->kw_gate; k->gain = p->kw_gain;
+    for (int i = 0; i < p->kw_nsec; ++i) k->f[i] = p->kw[i];
+}
 
 static int upload(void** dst, const void* src, size_t bytes) {
     CK(cudaMalloc(dst, bytes ? bytes : 1));
@@ -488,8 +519,9 @@ static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
     std::vector<float> h32(p->W);
     for (int i = 0; i < p->W; ++i) h32[i] = (float)d->meter_hann[i];
     rc = upload((void**)&p->hann32, h32.data(), h32.size() * sizeof(float)); if (rc) return rc;
-    build_biquad(d->kw_coeffs + 0, d->kw_coeffs + 3, &p->kw[0]);
-    build_biquad(d->kw_coeffs + 6, d->kw_coeffs + 9, &p->kw[1]);
+    build_biquad(d->kw_coeffs + 0, d->kw_coeffs + 3, 2, &p->kw_default[0]);
+    build_biquad(d->kw_coeffs + 6, d->kw_coeffs + 9, 2, &p->kw_default[1]);
+    set_weighting_k(p);
     rc = get_twiddles(p->device, ilog2(p->W) - 1, &p->tw_meter); if (rc) return rc;
     return OMEGA4_OK;
 }
@@ -545,6 +577,25 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
 }
 
 extern "C" long long omega4_plan_launches(const omega4_plan* p) { return p ? p->launches : 0; }
+
+extern "C" int omega4_plan_set_weighting(omega4_plan* p, const omega4_weighting* w) {
+    if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
+    if (!w) { set_weighting_k(p); return OMEGA4_OK; }
+    if (w->n_sections < 0 || w->n_sections > 4) return fail(OMEGA4_ERR_INVALID, "0..4 weighting sections");
+    if (w->blend && w->n_sections != 2) return fail(OMEGA4_ERR_INVALID, "the K blend needs exactly two sections");
+    KwBiquad tmp[4];
+    for (int i = 0; i < w->n_sections; ++i) {
+        const int order = w->order[i];
+        if (order != 1 && order != 2) return fail(OMEGA4_ERR_UNSUPPORTED, "weighting sections must be first or second order");
+        if (w->a[i][0] == 0.0 || w->a[i][1] == 0.0 || (order == 2 && w->a[i][2] == 0.0))
+            return fail(OMEGA4_ERR_UNSUPPORTED, "weighting sections need non-zero denominator coefficients");
+        build_biquad(w->b[i], w->a[i], order, &tmp[i]);
+    }
+    for (int i = 0; i < w->n_sections; ++i) p->kw[i] = tmp[i];
+    p->kw_nsec = w->n_sections; p->kw_blend = w->blend ? 1 : 0; p->kw_gate = w->rms_gate ? 1 : 0;
+    p->kw_gain = w->blend ? 1.0 : w->gain;
+    return OMEGA4_OK;
+}
 
 // event bracket helper
 struct Bracket {
@@ -636,7 +687,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
             k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
             k.hann = p->hann64; k.lufs_out = lufs; k.weighted_out = nullptr;
-            k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
+            fill_weighting(p, &k);
             Bracket b(p, ms, timing, "kweight_lufs");
             int rc = launch_kweight(k, ms);
             if (rc) return rc;
@@ -986,7 +1037,7 @@ extern "C" int omega4_meter_frames(omega4_plan* p, void* stream, int mem, const 
         k.x = d_fr; k.x_is_f64 = 1; k.ch_stride = 0; k.frame_stride = W; k.frame_off0 = 0;
         k.n_ch = 1; k.n_frames = n_frames; k.first_frame = 0; k.frames_per_warp = n_frames >= 64 ? 4 : 1;
         k.hann = nullptr; k.lufs_out = d_l; k.weighted_out = d_w;
-        k.f[0] = p->kw[0]; k.f[1] = p->kw[1];
+        fill_weighting(p, &k);
         p->launches++;
         rc = launch_kweight(k, s);
         if (rc) { tmp_w.release(); return rc; }

@@ -34,7 +34,7 @@ EXPORTS = (
     "omega4_plan_create", "omega4_plan_destroy", "omega4_analyze", "omega4_combine",
     "omega4_meter_frames", "omega4_meter_stats", "omega4_rfft_batch", "omega4_band_map",
     "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
-    "omega4_analyze_s16", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
+    "omega4_analyze_s16", "omega4_plan_set_weighting", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
 )
 
 
@@ -58,6 +58,14 @@ class PlanDesc(C.Structure):
         ("meter_hann", C.POINTER(C.c_double)),
         ("kw_coeffs", C.POINTER(C.c_double)),
         ("gate_threshold", C.c_double),
+    ]
+
+
+class Weighting(C.Structure):
+    _fields_ = [
+        ("n_sections", C.c_int), ("order", C.c_int * 4),
+        ("b", (C.c_double * 3) * 4), ("a", (C.c_double * 3) * 4),
+        ("blend", C.c_int), ("rms_gate", C.c_int), ("gain", C.c_double),
     ]
 
 
@@ -105,6 +113,8 @@ def lib() -> C.CDLL:
         l.omega4_analyze.argtypes = [vp, vp, ip, vp, ll, ip, ip, ip, vp, C.POINTER(vp), vp, vp, vp, vp, ip]
         l.omega4_analyze_s16.restype = ip
         l.omega4_analyze_s16.argtypes = [vp, vp, ip, vp, ll, ip, ip, ip, ip, vp, C.POINTER(vp), vp, vp, vp, vp, ip]
+        l.omega4_plan_set_weighting.restype = ip
+        l.omega4_plan_set_weighting.argtypes = [vp, C.POINTER(Weighting)]
         l.omega4_combine.restype = ip
         l.omega4_combine.argtypes = [vp, vp, ip, C.POINTER(vp), ip, vp]
         l.omega4_meter_frames.restype = ip

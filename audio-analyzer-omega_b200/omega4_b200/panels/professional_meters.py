@@ -7,9 +7,9 @@ true_peak_history, loudness_range_history, peak_hold_value, peak_hold_counter, t
 K-weighting (two zero-phase biquad passes as a block-parallel scan, fp64 state), the mean-square /
 LUFS conversion, the exact 4x FFT-interpolated true peak and the deque statistics (M/S/I/LRA/TP
 windows of 24/180/3600/60 frames) all run in libomega4_cuda.so; the deque contents live in a
-device-format state vector carried between calls.  Frames must have 2048 samples
-(FFT_SIZE_BASE, what the app feeds); other lengths and the A/C weighting modes are not
-implemented on the GPU yet and raise -- there is no CPU fallback.
+device-format state vector carried between calls.  The A / C / Z weighting modes (:74-127, 155-229)
+run through the same kernel as cascades of first/second-order zero-phase sections.  Frames must have
+2048 samples (FFT_SIZE_BASE, what the app feeds); other lengths raise -- there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -21,16 +21,20 @@ import numpy as np
 from .. import _native as N
 from ..plan import AnalysisPlan, BASELINE_CONFIGS, METER_KEYS
 
-_PLANS: Dict[Tuple[int, int], AnalysisPlan] = {}
+_PLANS: Dict[Tuple[int, int, str], AnalysisPlan] = {}
 
 
-def _meter_plan(sample_rate: int, device: int) -> AnalysisPlan:
-    key = (int(sample_rate), int(device))
+def _meter_plan(sample_rate: int, device: int, mode: str = "K") -> AnalysisPlan:
+    """One plan per (sample rate, device, weighting mode): the weighting is plan state."""
+    mode = mode if mode in ("K", "A", "C") else "Z"                 # apply_weighting's else branch (:228-229)
+    key = (int(sample_rate), int(device), mode)
     p = _PLANS.get(key)
     if p is None:
         # the FFT part of the plan is irrelevant for the meters; any valid configuration will do
         cfg = [c for c in BASELINE_CONFIGS if c[0][1] <= sample_rate / 2]
         p = AnalysisPlan(sample_rate, cfg, 512, min(20000, sample_rate / 2), device=device)
+        if mode != "K":
+            p.set_weighting(mode)
         _PLANS[key] = p
     return p
 
@@ -72,18 +76,27 @@ class ProfessionalMetering:
         n = int(self._state[0, 1])
         return deque(self._state[0, 8 + 3600:8 + 3600 + n].tolist(), maxlen=60)
 
-    def _require_k(self):
-        if self.weighting_mode not in ("K", "Z"):
-            raise N.Omega4CudaError(f"weighting mode {self.weighting_mode!r} is not implemented on the GPU "
-                                    "(K and Z are); there is no CPU fallback")
+    def _mode_plan(self, mode: Optional[str] = None) -> AnalysisPlan:
+        return _meter_plan(self.sample_rate, self.device, self.weighting_mode if mode is None else mode)
 
-    def apply_k_weighting(self, audio_data: np.ndarray) -> np.ndarray:
-        _, _, w = self._plan.meter_frames_host(np.asarray(audio_data, dtype=np.float64), want_weighted=True)
+    def _weighted(self, audio_data: np.ndarray, mode: str) -> np.ndarray:
+        _, _, w = self._mode_plan(mode).meter_frames_host(np.asarray(audio_data, dtype=np.float64), want_weighted=True)
         return w[0]
 
+    def apply_k_weighting(self, audio_data: np.ndarray) -> np.ndarray:
+        return self._weighted(audio_data, "K")
+
+    def apply_a_weighting(self, audio_data: np.ndarray) -> np.ndarray:
+        return self._weighted(audio_data, "A")
+
+    def apply_c_weighting(self, audio_data: np.ndarray) -> np.ndarray:
+        return self._weighted(audio_data, "C")
+
     def apply_weighting(self, audio_data: np.ndarray) -> np.ndarray:
-        self._require_k()
-        return self.apply_k_weighting(audio_data) if self.weighting_mode == "K" else audio_data
+        """(:219-229) 'K' / 'A' / 'C'; anything else is Z-weighting and returns the input itself."""
+        if self.weighting_mode in ("K", "A", "C"):
+            return self._weighted(audio_data, self.weighting_mode)
+        return audio_data
 
     def calculate_true_peak(self, audio_data: np.ndarray, oversampling: int = 4) -> float:
         if len(audio_data) == 0:
@@ -103,12 +116,8 @@ class ProfessionalMetering:
         """(:231-281) returns the same mutable dict object on every call, as the reference does."""
         if len(audio_data) == 0:
             return self.current_lufs
-        self._require_k()
         f = np.asarray(audio_data, dtype=np.float64)
-        li, tp, _ = self._plan.meter_frames_host(f)
-        if self.weighting_mode == "Z":
-            ms = float(np.mean(f ** 2))
-            li[0] = -0.691 + 10 * np.log10(ms) if ms > 1e-10 else -100.0
+        li, tp, _ = self._mode_plan().meter_frames_host(f)
         out = self._plan.meter_stats_host(li, tp, state=self._state, fresh=self._fresh)
         self._fresh = False
         for k, v in zip(METER_KEYS, out[0, 0]):

@@ -95,6 +95,7 @@ class AnalysisPlan:
         self.hann64 = np.hanning(self.meter_window).astype(np.float64)
         self.kw_coeffs = tables.k_weighting_coeffs(self.sample_rate)
         self._handle = None
+        self.weighting_mode = "K"
         self._create()
 
     # ------------------------------------------------------------------ lifecycle
@@ -148,6 +149,22 @@ class AnalysisPlan:
         if not self._handle:
             raise N.Omega4CudaError("plan is closed")
         return self._handle
+
+    def set_weighting(self, mode: str = "K"):
+        """ProfessionalMetering.weighting_mode for every later meter call on this plan:
+        'K' (default), 'A', 'C' or 'Z' (professional_meters.py:219-229)."""
+        prog = tables.weighting_program(mode, self.sample_rate)
+        w = N.Weighting()
+        w.n_sections = len(prog["sections"])
+        for i, (b, a) in enumerate(prog["sections"]):
+            w.order[i] = len(a) - 1
+            for j in range(len(b)):
+                w.b[i][j] = float(b[j])
+            for j in range(len(a)):
+                w.a[i][j] = float(a[j])
+        w.blend, w.rms_gate, w.gain = int(prog["blend"]), int(prog["rms_gate"]), float(prog["gain"])
+        N.check(N.lib().omega4_plan_set_weighting(self.handle, C.byref(w)), "omega4_plan_set_weighting")
+        self.weighting_mode = mode
 
     # ------------------------------------------------------------------ helpers
     def first_hop(self, n: int, hist: int = 0) -> int:

@@ -172,3 +172,38 @@ def k_weighting_coeffs(sample_rate: int) -> np.ndarray:
     hp_b, hp_a = butter2_highpass(38.0, sample_rate)
     sh_b, sh_a = butter2_highpass(1500.0, sample_rate)
     return np.concatenate([hp_b, hp_a, sh_b, sh_a]).astype(np.float64)
+
+
+def butter_lowhigh(order: int, fc: float, fs: float, btype: str):
+    """scipy.signal.butter(order, fc/(fs/2), btype), order 1 or 2, closed form (bilinear transform
+    with pre-warping) -- the sections of professional_meters.py:88-99, 118-121."""
+    k = np.tan(np.pi * fc / fs)
+    if order == 1:
+        a = np.array([1.0, (k - 1.0) / (k + 1.0)])
+        b = (np.array([1.0, -1.0]) if btype == "high" else np.array([k, k])) / (1.0 + k)
+        return b, a
+    norm = 1.0 / (1.0 + np.sqrt(2.0) * k + k * k)
+    a = np.array([1.0, 2.0 * (k * k - 1.0) * norm, (1.0 - np.sqrt(2.0) * k + k * k) * norm])
+    b = (np.array([1.0, -2.0, 1.0]) if btype == "high" else np.array([1.0, 2.0, 1.0]) * k * k) * norm
+    return b, a
+
+
+def weighting_program(mode: str, sample_rate: int):
+    """ProfessionalMetering.weighting_mode -> the cascade the CUDA meter kernel runs
+    (professional_meters.py:74-127 filters, :129-229 application): dict with ``sections`` [(b, a)],
+    ``blend`` (K's f + 0.3 (s - f)), ``rms_gate`` and ``gain``."""
+    nyq = sample_rate / 2
+    f1, f2, f3, f4 = 20.598997, 107.65265, 737.86223, 12194.217
+    if mode == "K":
+        return {"sections": [butter2_highpass(38.0, sample_rate), butter2_highpass(1500.0, sample_rate)],
+                "blend": 1, "rms_gate": 1, "gain": 1.0}
+    if mode == "A":
+        return {"sections": [butter_lowhigh(2, f1, sample_rate, "high"), butter_lowhigh(1, f2, sample_rate, "high"),
+                             butter_lowhigh(1, f3, sample_rate, "low"),
+                             butter_lowhigh(2, min(f4 / nyq, 0.99) * nyq, sample_rate, "low")],
+                "blend": 0, "rms_gate": 1, "gain": 2.5}
+    if mode == "C":
+        return {"sections": [butter_lowhigh(2, f1, sample_rate, "high"),
+                             butter_lowhigh(2, min(f4 / nyq, 0.99) * nyq, sample_rate, "low")],
+                "blend": 0, "rms_gate": 1, "gain": 1.0}
+    return {"sections": [], "blend": 0, "rms_gate": 0, "gain": 1.0}       # 'Z' and anything else (:228-229)

@@ -83,6 +83,27 @@ int omega4_device_count(void);
 omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int device);
 void omega4_plan_destroy(omega4_plan* plan);
 
+/* Frequency weighting of the meters: ProfessionalMetering.weighting_mode
+ * 'K' / 'A' / 'C' / 'Z' (professional_meters.py:74-127, 129-229).  A weighting is a cascade of up to
+ * four zero-phase sections, each scipy.signal.filtfilt(b, a, x) of order 1 or 2 with scipy's default
+ * odd padding (padlen 3 * (order + 1)):
+ *   K: 2 sections, blend = 1      -> out = f0 + 0.3 (f1 - f0)            (:137-151; the plan's default)
+ *   A: hp1, hp2, lp1, lp2, gain 2.5                                      (:166-190)
+ *   C: hp, lp, gain 1                                                    (:205-216)
+ *   Z: n_sections = 0, rms_gate = 0                                      (:228-229)
+ * rms_gate: frames with rms < 1e-6 weigh to zeros (:132-134, :158-160, :197-199).
+ * Affects omega4_analyze and omega4_meter_frames on this plan from the next call on; NULL restores K. */
+typedef struct omega4_weighting {
+    int n_sections;
+    int order[4];
+    double b[4][3];
+    double a[4][3];
+    int blend;
+    int rms_gate;
+    double gain;
+} omega4_weighting;
+int omega4_plan_set_weighting(omega4_plan* plan, const omega4_weighting* weighting);
+
 /* The whole hot path over a batch: replaces, per channel and hop,
  *   MultiResolutionFFT.process_audio_chunk + combine_results_optimized (multi_resolution_fft.py:228,335)
  *   ProfessionalMetering.calculate_lufs on the Hann-windowed last 2048 samples (professional_meters.py:231)

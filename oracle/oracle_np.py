@@ -594,6 +594,77 @@ def apply_k_weighting(frames: np.ndarray, coeffs) -> np.ndarray:
     return out
 
 
+# --------------------------------------------------------------------------------------
+# A / C / Z weighting (professional_meters.py:74-127, 155-229) -- SURVEY.md section 8f rank 2
+# --------------------------------------------------------------------------------------
+def butter_lowhigh(order: int, fc: float, fs: float, btype: str):
+    """scipy.signal.butter(order, fc/(fs/2), btype) for order 1 or 2, closed form of the bilinear
+    transform with pre-warping (K = tan(pi fc/fs))."""
+    k = np.tan(np.pi * fc / fs)
+    if order == 1:
+        a = np.array([1.0, (k - 1.0) / (k + 1.0)])
+        b = (np.array([1.0, -1.0]) if btype == "high" else np.array([k, k])) / (1.0 + k)
+        return b, a
+    norm = 1.0 / (1.0 + np.sqrt(2.0) * k + k * k)
+    a = np.array([1.0, 2.0 * (k * k - 1.0) * norm, (1.0 - np.sqrt(2.0) * k + k * k) * norm])
+    b = (np.array([1.0, -2.0, 1.0]) if btype == "high" else np.array([1.0, 2.0, 1.0]) * k * k) * norm
+    return b, a
+
+
+def a_weighting_sections(sample_rate: int):
+    """create_a_weighting_filter (professional_meters.py:74-107): hp1, hp2, lp1, lp2 as (b, a) pairs."""
+    nyq = sample_rate / 2
+    f1, f2, f3, f4 = 20.598997, 107.65265, 737.86223, 12194.217
+    return [butter_lowhigh(2, f1, sample_rate, "high"), butter_lowhigh(1, f2, sample_rate, "high"),
+            butter_lowhigh(1, f3, sample_rate, "low"), butter_lowhigh(2, min(f4 / nyq, 0.99) * nyq, sample_rate, "low")]
+
+
+def c_weighting_sections(sample_rate: int):
+    """create_c_weighting_filter (professional_meters.py:109-127): hp, lp."""
+    nyq = sample_rate / 2
+    f1, f4 = 20.598997, 12194.217
+    return [butter_lowhigh(2, f1, sample_rate, "high"), butter_lowhigh(2, min(f4 / nyq, 0.99) * nyq, sample_rate, "low")]
+
+
+def filtfilt_any(b, a, x: np.ndarray) -> np.ndarray:
+    """scipy.signal.filtfilt(b, a, x), defaults, for first- or second-order (b, a): padlen =
+    3 * max(len(a), len(b)) (6 or 9); a first-order section is the biquad with b2 = a2 = 0."""
+    padlen = 3 * max(len(a), len(b))
+    b3 = np.concatenate([np.asarray(b, dtype=np.float64), np.zeros(3 - len(b))])
+    a3 = np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(3 - len(a))])
+    zi = lfilter_zi2(b3, a3)
+    ext = odd_ext(np.asarray(x, dtype=np.float64), padlen)
+    y = lfilter_tdf2(b3, a3, ext, zi * ext[..., :1])
+    y = lfilter_tdf2(b3, a3, y[..., ::-1], zi * y[..., -1:])
+    return y[..., ::-1][..., padlen:-padlen]
+
+
+def apply_weighting(frames: np.ndarray, mode: str, sample_rate: int = 48000) -> np.ndarray:
+    """apply_weighting (professional_meters.py:219-229) for 'K', 'A' (:155-192), 'C' (:194-217), 'Z'."""
+    x = np.asarray(frames, dtype=np.float64)
+    if mode == "K":
+        return apply_k_weighting(x, k_weighting_coeffs(sample_rate))
+    if mode == "Z" or mode not in ("A", "C"):
+        return x
+    rms = np.sqrt(np.mean(x ** 2, axis=-1))
+    y = x.copy()
+    for b, a in (a_weighting_sections(sample_rate) if mode == "A" else c_weighting_sections(sample_rate)):
+        y = filtfilt_any(b, a, y)
+    if mode == "A":
+        y = y * 2.5                                              # (:190)
+    y[rms < 1e-6] = 0.0                                          # (:158-160, :197-199)
+    return y
+
+
+def lufs_instantaneous_mode(frames: np.ndarray, mode: str, sample_rate: int = 48000) -> np.ndarray:
+    """calculate_lufs core (:236-246) with the selected weighting."""
+    w = apply_weighting(frames, mode, sample_rate)
+    ms = np.mean(w ** 2, axis=-1)
+    with np.errstate(divide="ignore"):
+        l = -0.691 + 10.0 * np.log10(ms)
+    return np.where(ms > 1e-10, l, -100.0)
+
+
 def resample_fft(x: np.ndarray, factor: int = 4) -> np.ndarray:
     """scipy.signal.resample(x, factor*len(x)) for real x of even length (FFT method):
     X = rfft(x); X[N/2] *= 0.5; irfft(zero-padded X, factor*N) * factor."""

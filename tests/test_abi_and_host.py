@@ -226,3 +226,19 @@ def test_app_post_tables_match_oracle():
         assert np.array_equal(tables.app_compensation_gains(f, ct, vs), O.app_compensation_gains(f, ct, vs))
     bands = tables.mel_band_indices(48000, 2048, 512)
     assert np.array_equal(tables.app_smoothing_factors(bands, 48000, 2048), O.app_smoothing_factors(bands, 48000, 2048))
+
+
+def test_weighting_programs_match_oracle_sections():
+    from omega4_b200 import tables
+    from oracle import oracle_np as O
+    for sr in (48000, 96000, 44100):
+        for mode, ref in (("A", O.a_weighting_sections(sr)), ("C", O.c_weighting_sections(sr))):
+            prog = tables.weighting_program(mode, sr)
+            assert len(prog["sections"]) == len(ref) and prog["blend"] == 0 and prog["rms_gate"] == 1
+            for (b, a), (rb, ra) in zip(prog["sections"], ref):
+                assert np.array_equal(b, rb) and np.array_equal(a, ra)
+        k = tables.weighting_program("K", sr)
+        assert k["blend"] == 1 and len(k["sections"]) == 2
+        z = tables.weighting_program("Z", sr)
+        assert z["sections"] == [] and z["rms_gate"] == 0
+    assert tables.weighting_program("A", 48000)["gain"] == 2.5

@@ -378,6 +378,43 @@ def test_meters_known_answers(plan, golden):
     assert np.abs(w[:2] - ref).max() < 1e-7
 
 
+# ------------------------------------------------------------------ section 8f rank 2: A / C / Z weighting
+@pytest.mark.parametrize("mode", ["A", "C", "Z"])
+def test_meter_weighting_modes_golden(golden, mode):
+    """ProfessionalMetering with weighting_mode A / C / Z (professional_meters.py:74-127, 155-229):
+    cascades of first/second-order filtfilt sections through the same block-scan kernel."""
+    from omega4_b200.panels.professional_meters import ProfessionalMetering
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
+    g = golden("meters_weighting.npz")
+    x = g["x"]
+    m = ProfessionalMetering(48000)
+    m.weighting_mode = mode
+    hops = list(g["weighted_hops"])
+    for k in range(3, len(x) // HOP):
+        frame = x[(k + 1) * HOP - W:(k + 1) * HOP] * np.hanning(W)
+        if k in hops:
+            w = m.apply_weighting(frame)
+            ref = g[f"weighted_{mode}"][hops.index(k)]
+            assert np.abs(w - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max()), (mode, k)
+        d = m.calculate_lufs(frame)
+        assert abs(m.lufs_momentary_history[-1] - g[f"lufs_inst_{mode}"][k - 3]) <= 1e-5, (mode, k)
+        _meters_close([d[key] for key in O.METER_KEYS], g[f"meters_{mode}"][k - 3], f"{mode} hop {k}")
+    quiet = x[:W] * np.hanning(W) * 1e-7                                 # rms gate: zeros in A / C, identity in Z
+    wq = m.apply_weighting(quiet)
+    assert np.array_equal(wq, quiet) if mode == "Z" else np.all(wq == 0)
+    # the batch path with the plan switched to the same mode
+    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
+    p.set_weighting(mode)
+    out = p.analyze_host(x[None, :], want_combined=False, want_series=True)
+    assert np.abs(out["lufs_inst"][0, 3:] - g[f"lufs_inst_{mode}"]).max() <= 1e-5
+    _meters_close(out["meters"][0, 3:], g[f"meters_{mode}"], f"batch {mode}")
+    p.set_weighting("K")
+    k_out = p.analyze_host(x[None, :], want_combined=False, want_series=True)
+    ref = O.analyze_channel(x, 48000, O.BASELINE_CONFIGS)
+    assert np.abs(k_out["lufs_inst"][0, 3:] - ref["lufs_inst"][3:]).max() <= 1e-5        # back to K
+    p.close()
+
+
 # ------------------------------------------------------------------ reference-shaped shims
 def test_shim_multires_chunks_and_appfeed(golden):
     from omega4_b200.audio.multi_resolution_fft import MultiResolutionFFT, FFTConfig, FFTResult, WindowType
@@ -518,9 +555,6 @@ def test_shim_professional_metering(golden):
     np.testing.assert_allclose(m.k_weighting_filter["hp_a"], golden("meters_known.npz")["hp_a"], atol=2e-15)
     with pytest.raises(Omega4CudaError):
         m.calculate_lufs(np.zeros(480))                                 # unsupported length: loud, no CPU path
-    m.weighting_mode = "A"
-    with pytest.raises(Omega4CudaError):
-        m.calculate_lufs(np.zeros(W))
     gp = golden("meters_panel.npz")
     p = ProfessionalMetersPanel(48000)
     assert p.get_results()["lufs"] is None

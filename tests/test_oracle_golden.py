@@ -307,3 +307,35 @@ def test_app_post_processing_matches_reference_block(golden, variant, kw):
         np.testing.assert_allclose(peak, g["peak_" + variant][k], rtol=0, atol=1.2e-7)
         np.testing.assert_allclose(band, g["band_" + variant][k], rtol=0, atol=2.4e-7)
     assert float(g["band_default"].max()) == 1.0 and float(g["band_default"].min()) == 0.0
+
+
+# ---------------------------------------------------------------- section 8f rank 2: A / C / Z weighting
+def test_a_c_weighting_coefficients_and_frames(golden):
+    """oracle closed-form Butterworth sections and apply_weighting vs the unmodified reference."""
+    g = golden("meters_weighting.npz")
+    for name, (b, a) in zip(("hp1", "hp2", "lp1", "lp2"), O.a_weighting_sections(48000)):
+        np.testing.assert_allclose(b, g[f"A_{name}_b"], rtol=0, atol=3e-15)
+        np.testing.assert_allclose(a, g[f"A_{name}_a"], rtol=0, atol=3e-15)
+    for name, (b, a) in zip(("hp", "lp"), O.c_weighting_sections(48000)):
+        np.testing.assert_allclose(b, g[f"C_{name}_b"], rtol=0, atol=3e-15)
+        np.testing.assert_allclose(a, g[f"C_{name}_a"], rtol=0, atol=3e-15)
+    x = g["x"]
+    hops = list(g["weighted_hops"])
+    frames = np.stack([x[(k + 1) * HOP - W:(k + 1) * HOP] * np.hanning(W) for k in range(3, len(x) // HOP)])
+    for mode in ("A", "C", "Z"):
+        w = O.apply_weighting(frames[[k - 3 for k in hops]], mode)
+        assert np.abs(w - g[f"weighted_{mode}"]).max() <= 1e-11, mode
+        li = O.lufs_instantaneous_mode(frames, mode)
+        assert np.abs(li - g[f"lufs_inst_{mode}"]).max() <= 1e-9, mode
+    # frames with rms < 1e-6 weigh to zeros in A and C (:158-160, :197-199) but pass through in Z
+    quiet = frames[:1] * 1e-7
+    assert np.all(O.apply_weighting(quiet, "A") == 0) and np.all(O.apply_weighting(quiet, "C") == 0)
+    assert np.array_equal(O.apply_weighting(quiet, "Z"), quiet)
+
+
+def test_restated_first_order_filtfilt_matches_scipy():
+    sps = pytest.importorskip("scipy.signal")
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 2048))
+    for b, a in O.a_weighting_sections(48000):
+        np.testing.assert_allclose(O.filtfilt_any(b, a, x), sps.filtfilt(b, a, x), rtol=0, atol=1e-9)   # 20.6 Hz poles: 1e-11 round-off
