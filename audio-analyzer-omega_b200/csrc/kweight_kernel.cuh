@@ -41,17 +41,26 @@ constexpr int KW_NSUB = 4;
 constexpr int KW_SUBMAX = 17;
 __host__ __device__ constexpr int kw_off(int j) { return j == 0 ? 0 : 17 + 16 * (j - 1); }   // 0,17,33,49,65
 
-struct KwBiquad {
-    double b0, b1, b2, a1, a2;
-    double yi0, yi1;                // (y[-1], y[-2]) per unit x0, equivalent to scipy's lfilter_zi state
-    double phi[5][4];               // (C^65)^(2^j), row major [[p00,p01],[p10,p11]], C = [[-a1,-a2],[1,0]]
-    double cinv_f[4];               // C^-(9 - pad): forward start moved back over the unused leading slots
-    double cinv_b[4];               // C^-(14 + 9 - pad): backward start moved back over the trailing slack
+template <typename T>
+struct KwBiquadT {
+    T b0, b1, b2, a1, a2;
+    T yi0, yi1;                     // (y[-1], y[-2]) per unit x0, equivalent to scipy's lfilter_zi state
+    T phi[5][4];                    // (C^65)^(2^j), row major [[p00,p01],[p10,p11]], C = [[-a1,-a2],[1,0]]
+    T cinv_f[4];                    // C^-(9 - pad): forward start moved back over the unused leading slots
+    T cinv_b[4];                    // C^-(14 + 9 - pad): backward start moved back over the trailing slack
     int pad;                        // filtfilt padlen = 3 * max(len(a), len(b)): 9 (biquad) or 6 (first order)
     int _align;
-    double c16[4], c17[4];          // C^16, C^17: transitions over one sub-chunk
-    double g[KW_SUBMAX][2];         // g[i] = first row of C^(i+1)  (homogeneous output response)
+    T c16[4], c17[4];               // C^16, C^17: transitions over one sub-chunk
+    T g[KW_SUBMAX][2];              // g[i] = first row of C^(i+1)  (homogeneous output response)
 };
+using KwBiquad = KwBiquadT<double>;
+using KwBiquadF = KwBiquadT<float>;   // float32 mirror, used for well-conditioned sections only
+
+template <typename T> struct KwVec2;
+template <> struct KwVec2<double> { using type = double2; };
+template <> struct KwVec2<float> { using type = float2; };
+__device__ __forceinline__ double2 kw_make2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ float2 kw_make2(float x, float y) { return make_float2(x, y); }
 
 struct KweightArgs {
     const void* x;                  // float samples (hop mode) or double frames (frames mode)
@@ -74,41 +83,52 @@ struct KweightArgs {
     int rms_gate;
     int _align;
     double gain;
+    // sections [f32_from, n_sec) run in float32: their poles are far from the unit circle (|z| < 0.95),
+    // where float32 state costs ~1e-6 relative error -- 1e-5 LU against the 0.01 LU parity bar -- and
+    // half the pipe time of float64.  Sections before f32_from (the 38 Hz / 20.6 Hz high-passes with
+    // poles at radius 0.997) keep float64 state.  Kernels that return the weighted frame use float64
+    // throughout (f32_from = n_sec).
+    int f32_from;
+    int _align2;
     KwBiquad f[4];
+    KwBiquadF ff[4];
 };
 
-__device__ __forceinline__ double2 mat2_apply(const double* m, double2 s) {
-    return make_double2(fma(m[0], s.x, m[1] * s.y), fma(m[2], s.x, m[3] * s.y));
+template <typename T>
+__device__ __forceinline__ typename KwVec2<T>::type mat2_apply(const T* m, typename KwVec2<T>::type s) {
+    return kw_make2(fma(m[0], s.x, m[1] * s.y), fma(m[2], s.x, m[3] * s.y));
 }
 
 // one lfilter pass over the warp's 2066-sample sequence held as r[65] per lane.
-template <bool BACKWARD>
-__device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, int lane) {
+template <bool BACKWARD, typename T>
+__device__ __forceinline__ void kw_pass(T (&r)[KW_L], const KwBiquadT<T>& c, int lane) {
+    using V2 = typename KwVec2<T>::type;
+    const T zero = (T)0;
     // scan position of this lane: 0 is processed first
     const int pos = BACKWARD ? 31 - lane : lane;
     // the sample whose value scales the steady-state initial condition: first / last sample of the
     // padded sequence, which starts 9 - pad slots into lane 0 and ends 9 - pad slots before KW_LAST
     const bool short_pad = c.pad < KW_PAD;                           // pad 6: three unused slots at either end
     constexpr int SH = KW_PAD - 6;
-    double x0 = BACKWARD ? __shfl_sync(0xffffffffu, short_pad ? r[KW_LAST - SH] : r[KW_LAST], 31)
+    T x0 = BACKWARD ? __shfl_sync(0xffffffffu, short_pad ? r[KW_LAST - SH] : r[KW_LAST], 31)
                          : __shfl_sync(0xffffffffu, short_pad ? r[SH] : r[0], 0);
     if (BACKWARD && lane == 31) {
 #pragma unroll
-        for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = 0.0;
+        for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = zero;
         if (short_pad) {
 #pragma unroll
-            for (int i = KW_LAST - SH + 1; i <= KW_LAST; ++i) r[i] = 0.0;
+            for (int i = KW_LAST - SH + 1; i <= KW_LAST; ++i) r[i] = zero;
         }
     }
-    double2 s_init = make_double2(c.yi0 * x0, c.yi1 * x0);
-    s_init = mat2_apply(BACKWARD ? c.cinv_b : c.cinv_f, s_init);
+    V2 s_init = kw_make2(c.yi0 * x0, c.yi1 * x0);
+    s_init = mat2_apply<T>(BACKWARD ? c.cinv_b : c.cinv_f, s_init);
 
     // sub-chunk m (processing order) = index range j: forward j = m, backward j = 3 - m
     // length of sub-chunk m in processing order: forward 17,16,16,16 ; backward 16,16,16,17
-    double xa[KW_NSUB], xb[KW_NSUB];      // the two inputs preceding each sub-chunk (processing order)
+    T xa[KW_NSUB], xb[KW_NSUB];      // the two inputs preceding each sub-chunk (processing order)
     xa[0] = BACKWARD ? __shfl_down_sync(0xffffffffu, r[0], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 1], 1);
     xb[0] = BACKWARD ? __shfl_down_sync(0xffffffffu, r[1], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 2], 1);
-    if (pos == 0) { xa[0] = 0.0; xb[0] = 0.0; }
+    if (pos == 0) { xa[0] = zero; xb[0] = zero; }
 #pragma unroll
     for (int m = 1; m < KW_NSUB; ++m) {
         const int j = BACKWARD ? KW_NSUB - 1 - m : m;
@@ -116,9 +136,9 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
         xb[m] = BACKWARD ? r[kw_off(j + 1) + 1] : r[kw_off(j) - 2];
     }
     // 1. zero-state sweeps, direct form I, four independent chains
-    double y1[KW_NSUB], y2[KW_NSUB];
+    T y1[KW_NSUB], y2[KW_NSUB];
 #pragma unroll
-    for (int m = 0; m < KW_NSUB; ++m) { y1[m] = 0.0; y2[m] = 0.0; }
+    for (int m = 0; m < KW_NSUB; ++m) { y1[m] = zero; y2[m] = zero; }
 #pragma unroll
     for (int n = 0; n < KW_SUBMAX; ++n) {
 #pragma unroll
@@ -127,10 +147,10 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
             const int len = kw_off(j + 1) - kw_off(j);
             if (n < len) {
                 const int i = BACKWARD ? kw_off(j + 1) - 1 - n : kw_off(j) + n;
-                const double x = r[i];
-                const double u = fma(c.b0, x, fma(c.b1, xa[m], c.b2 * xb[m]));
-                const double t = fma(-c.a2, y2[m], u);
-                const double y = fma(-c.a1, y1[m], t);
+                const T x = r[i];
+                const T u = fma(c.b0, x, fma(c.b1, xa[m], c.b2 * xb[m]));
+                const T t = fma(-c.a2, y2[m], u);
+                const T y = fma(-c.a1, y1[m], t);
                 xb[m] = xa[m]; xa[m] = x;
                 y2[m] = y1[m]; y1[m] = y;
                 r[i] = y;
@@ -138,30 +158,30 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
         }
     }
     // lane aggregate: zero-state end state of the whole 65-sample chunk
-    double2 v = make_double2(y1[0], y2[0]);
+    V2 v = kw_make2(y1[0], y2[0]);
 #pragma unroll
     for (int m = 1; m < KW_NSUB; ++m) {
         const int j = BACKWARD ? KW_NSUB - 1 - m : m;
-        const double* cm = (kw_off(j + 1) - kw_off(j) == 17) ? c.c17 : c.c16;
-        double2 q = mat2_apply(cm, v);
-        v = make_double2(q.x + y1[m], q.y + y2[m]);
+        const T* cm = (kw_off(j + 1) - kw_off(j) == 17) ? c.c17 : c.c16;
+        V2 q = mat2_apply<T>(cm, v);
+        v = kw_make2(q.x + y1[m], q.y + y2[m]);
     }
     // 2. scan of chunk end states across lanes
     if (pos == 0) {
-        double2 q = mat2_apply(c.phi[0], s_init);
+        V2 q = mat2_apply<T>(c.phi[0], s_init);
         v.x += q.x; v.y += q.y;
     }
 #pragma unroll
     for (int jj = 0; jj < 5; ++jj) {
         const int d = 1 << jj;
-        double rx = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, d) : __shfl_up_sync(0xffffffffu, v.x, d);
-        double ry = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, d) : __shfl_up_sync(0xffffffffu, v.y, d);
+        T rx = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, d) : __shfl_up_sync(0xffffffffu, v.x, d);
+        T ry = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, d) : __shfl_up_sync(0xffffffffu, v.y, d);
         if (pos >= d) {
-            double2 q = mat2_apply(c.phi[jj], make_double2(rx, ry));
+            V2 q = mat2_apply<T>(c.phi[jj], kw_make2(rx, ry));
             v.x += q.x; v.y += q.y;
         }
     }
-    double2 sin[KW_NSUB];
+    V2 sin[KW_NSUB];
     sin[0].x = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, 1) : __shfl_up_sync(0xffffffffu, v.x, 1);
     sin[0].y = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, 1) : __shfl_up_sync(0xffffffffu, v.y, 1);
     if (pos == 0) sin[0] = s_init;
@@ -169,9 +189,9 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
 #pragma unroll
     for (int m = 1; m < KW_NSUB; ++m) {
         const int jp = BACKWARD ? KW_NSUB - m : m - 1;              // index range of sub-chunk m-1
-        const double* cm = (kw_off(jp + 1) - kw_off(jp) == 17) ? c.c17 : c.c16;
-        double2 q = mat2_apply(cm, sin[m - 1]);
-        sin[m] = make_double2(q.x + y1[m - 1], q.y + y2[m - 1]);
+        const T* cm = (kw_off(jp + 1) - kw_off(jp) == 17) ? c.c17 : c.c16;
+        V2 q = mat2_apply<T>(cm, sin[m - 1]);
+        sin[m] = kw_make2(q.x + y1[m - 1], q.y + y2[m - 1]);
     }
     // 3. homogeneous correction
 #pragma unroll
@@ -190,15 +210,16 @@ __device__ __forceinline__ void kw_pass(double (&r)[KW_L], const KwBiquad& c, in
 
 // odd reflection padding of the frame held at ext positions [9, 2057): lane 0 owns ext[0..9),
 // lane 31 owns ext[2057..2066) at local 42..50.
-__device__ __forceinline__ void kw_odd_pad(double (&r)[KW_L], int lane, int pad) {
+template <typename T>
+__device__ __forceinline__ void kw_odd_pad(T (&r)[KW_L], int lane, int pad) {
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[j] = (j >= KW_PAD - pad) ? 2.0 * r[KW_PAD] - r[2 * KW_PAD - j] : 0.0;
+        for (int j = 0; j < KW_PAD; ++j) r[j] = (j >= KW_PAD - pad) ? (T)2 * r[KW_PAD] - r[2 * KW_PAD - j] : (T)0;
     }
     if (lane == 31) {
         constexpr int E = KW_LAST - KW_PAD;     // 41: local index of the frame's last sample
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[E + 1 + j] = (j < pad) ? 2.0 * r[E] - r[E - 1 - j] : 0.0;
+        for (int j = 0; j < KW_PAD; ++j) r[E + 1 + j] = (j < pad) ? (T)2 * r[E] - r[E - 1 - j] : (T)0;
     }
 }
 
@@ -211,14 +232,15 @@ constexpr int KW_WARPS = 4;
 constexpr int KW_STG_SHIFT = 3;
 constexpr int KW_STG = 32 * KW_L + 16;          // 2096 floats per warp
 
-__device__ __forceinline__ void kw_zero_pads(double (&r)[KW_L], int lane) {
+template <typename T>
+__device__ __forceinline__ void kw_zero_pads(T (&r)[KW_L], int lane) {
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < KW_PAD; ++i) r[i] = 0.0;
+        for (int i = 0; i < KW_PAD; ++i) r[i] = (T)0;
     }
     if (lane == 31) {
 #pragma unroll
-        for (int i = KW_LAST - KW_PAD + 1; i < KW_L; ++i) r[i] = 0.0;
+        for (int i = KW_LAST - KW_PAD + 1; i < KW_L; ++i) r[i] = (T)0;
     }
 }
 
@@ -292,13 +314,14 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
         double ms = 0.0;
         if (!gated) {                                                  // warp-uniform
             float* fl = stg + KW_STG_SHIFT + KW_L * lane;
-            // the two filtfilt calls share one code body (loop not unrolled: halves the instruction
-            // footprint -- ncu showed 14 % instruction-fetch stalls with both inlined)
+            // the filtfilt calls of one precision share one code body (loop not unrolled: halves the
+            // instruction footprint -- ncu showed 14 % instruction-fetch stalls with both inlined)
+            const int n64 = WEIGHTED ? a.n_sec : min(a.f32_from, a.n_sec);
 #pragma unroll 1
-            for (int fi = 0; fi < a.n_sec; ++fi) {
+            for (int fi = 0; fi < n64; ++fi) {
                 kw_odd_pad(r, lane, a.f[fi].pad);
-                kw_pass<false>(r, a.f[fi], lane);
-                kw_pass<true>(r, a.f[fi], lane);
+                kw_pass<false, double>(r, a.f[fi], lane);
+                kw_pass<true, double>(r, a.f[fi], lane);
                 kw_zero_pads(r, lane);
                 if (fi == 0 && a.blend) {
                     // stash f (first filtfilt output) as fp32 with zeros at the pad positions;
@@ -308,17 +331,45 @@ kweight_kernel(const __grid_constant__ KweightArgs a) {
                 }
             }
             double acc = 0.0;
+            if (!WEIGHTED && n64 < a.n_sec) {
+                // well-conditioned tail of the cascade in float32
+                float rf[KW_L];
 #pragma unroll
-            for (int i = 0; i < KW_L; ++i) {
-                double w;
-                if (a.blend) {
-                    const double fv = (double)fl[i];
-                    w = fma(r[i] - fv, 0.3, fv);                       // f + (s - f) * 0.3 ; 0 at the pads
-                } else {
-                    w = r[i] * a.gain;                                 // cascade (A: x 2.5, C / Z: x 1)
+                for (int i = 0; i < KW_L; ++i) rf[i] = (float)r[i];
+#pragma unroll 1
+                for (int fi = n64; fi < a.n_sec; ++fi) {
+                    kw_odd_pad(rf, lane, a.ff[fi].pad);
+                    kw_pass<false, float>(rf, a.ff[fi], lane);
+                    kw_pass<true, float>(rf, a.ff[fi], lane);
+                    kw_zero_pads(rf, lane);
                 }
-                acc = fma(w, w, acc);
-                if (WEIGHTED) r[i] = w;
+                const float gain = (float)a.gain;
+                float accf = 0.f;
+#pragma unroll
+                for (int i = 0; i < KW_L; ++i) {
+                    float w;
+                    if (a.blend) {
+                        const float fv = fl[i];
+                        w = fmaf(rf[i] - fv, 0.3f, fv);                // f + (s - f) * 0.3 ; 0 at the pads
+                    } else {
+                        w = rf[i] * gain;
+                    }
+                    accf = fmaf(w, w, accf);
+                }
+                acc = (double)accf;
+            } else {
+#pragma unroll
+                for (int i = 0; i < KW_L; ++i) {
+                    double w;
+                    if (a.blend) {
+                        const double fv = (double)fl[i];
+                        w = fma(r[i] - fv, 0.3, fv);                   // f + (s - f) * 0.3 ; 0 at the pads
+                    } else {
+                        w = r[i] * a.gain;                             // cascade (A: x 2.5, C / Z: x 1)
+                    }
+                    acc = fma(w, w, acc);
+                    if (WEIGHTED) r[i] = w;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -328,9 +328,32 @@ static void set_weighting_k(omega4_plan* p) {
     p->kw_nsec = 2; p->kw_blend = 1; p->kw_gate = 1; p->kw_gain = 1.0;
 }
 
+static double max_pole_radius(const KwBiquad& q) {
+    if (q.a2 == 0.0) return fabs(q.a1);
+    const double disc = q.a1 * q.a1 - 4.0 * q.a2;
+    if (disc < 0.0) return sqrt(q.a2);
+    return fmax(fabs(-q.a1 + sqrt(disc)), fabs(-q.a1 - sqrt(disc))) * 0.5;
+}
+
+static void to_float(const KwBiquad& s, KwBiquadF* d) {
+    d->b0 = (float)s.b0; d->b1 = (float)s.b1; d->b2 = (float)s.b2; d->a1 = (float)s.a1; d->a2 = (float)s.a2;
+    d->yi0 = (float)s.yi0; d->yi1 = (float)s.yi1; d->pad = s.pad; d->_align = 0;
+    for (int j = 0; j < 5; ++j) for (int e = 0; e < 4; ++e) d->phi[j][e] = (float)s.phi[j][e];
+    for (int e = 0; e < 4; ++e) {
+        d->cinv_f[e] = (float)s.cinv_f[e]; d->cinv_b[e] = (float)s.cinv_b[e];
+        d->c16[e] = (float)s.c16[e]; d->c17[e] = (float)s.c17[e];
+    }
+    for (int i = 0; i < KW_SUBMAX; ++i) { d->g[i][0] = (float)s.g[i][0]; d->g[i][1] = (float)s.g[i][1]; }
+}
+
 static void fill_weighting(const omega4_plan* p, KweightArgs* k) {
     k->n_sec = p->kw_nsec; k->blend = p->kw_blend; k->rms_gate = p->kw_gate; k->gain = p->kw_gain;
-    for (int i = 0; i < p->kw_nsec; ++i) k->f[i] = p->kw[i];
+    for (int i = 0; i < p->kw_nsec; ++i) { k->f[i] = p->kw[i]; to_float(p->kw[i], &k->ff[i]); }
+    // trailing sections whose poles stay inside |z| < 0.95 run in float32 (kweight_kernel.cuh); the first
+    // section always keeps float64 state
+    int from = p->kw_nsec;
+    while (from > 1 && max_pole_radius(p->kw[from - 1]) < 0.95) --from;
+    k->f32_from = getenv("OMEGA4_KW_F64") ? p->kw_nsec : from;
 }
 
 static int upload(void** dst, const void* src, size_t bytes) {

@@ -1,0 +1,8 @@
+#!/bin/bash
+# usage: tools/run_prof.sh TAG   -- full bench, small plain bench, ncu launch list, ncu --set full of one step
+TAG=${1:-r01x}
+python bench.py > gpurun_out/${TAG}_full.log 2> gpurun_out/${TAG}_full.err
+python bench.py --steps 3 --warmup 3 --streams 128 --seconds 20 --no-cpu --no-e2e > gpurun_out/${TAG}_small_plain.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --streams 128 --seconds 20 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -s 25 -c 8 -o gpurun_out/prof_${TAG} -f python bench.py --steps 1 --warmup 3 --streams 128 --seconds 20 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -c 400 gpurun_out/${TAG}_full.log
