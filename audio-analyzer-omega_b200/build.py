@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "omega4_b200", "libomega4_cuda.so")
 SOURCES = ["omega4_cuda.cu"]
-HEADERS = ["bars_kernel.cuh", "blockdft_kernel.cuh", "fft_core.cuh", "multires_kernel.cuh", "truepeak_kernel.cuh", "kweight_kernel.cuh",
+HEADERS = ["bars_kernel.cuh", "blockdft_kernel.cuh", "blockdft_tc_kernel.cuh", "fft_core.cuh", "multires_kernel.cuh", "truepeak_kernel.cuh", "kweight_kernel.cuh",
            "stats_kernel.cuh", "misc_kernels.cuh", os.path.join("..", "..", "include", "omega4_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

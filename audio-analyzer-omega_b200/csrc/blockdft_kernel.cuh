@@ -170,7 +170,7 @@ inline size_t blockdft_gemm_smem_bytes() {
 // segments of combine_results_optimized straight into the combined row.
 // One CTA = BD_FA consecutive frames of one channel; the Q rows they share are staged in smem.
 // ---------------------------------------------------------------------------------------------
-constexpr int BD_FA = 64;
+constexpr int BD_FA_MAX = 64;        // frames per CTA: 64, 32 or 16, whichever keeps the staged Q rows under ~40 KB
 
 struct BlockDftAsmArgs {
     const float* Q;            // [n_ch][nb][qs]
@@ -188,6 +188,7 @@ struct BlockDftAsmArgs {
     const int* tb_pos;         // [n_tb] position of the lower FFT bin in the needed-bin list, -1: write 0
     const float* tb_frac;      // [n_tb]
     float wnum, wden;
+    int fa;                    // frames per CTA
 };
 
 __global__ void __launch_bounds__(256)
@@ -195,14 +196,14 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nc = a.nk * a.nt;                           // complex columns of this resolution
     const int rs = nc | 1;                                // odd float2 row stride: conflict-free across frames
-    float2* Qs = reinterpret_cast<float2*>(smem_raw);     // [BD_FA + B - 1][rs]
-    float2* Ts = Qs + (size_t)(BD_FA + a.B - 1) * rs;     // [nk][B][nt]
-    float* mags = reinterpret_cast<float*>(Ts + (size_t)a.nk * a.B * a.nt);   // [BD_FA][nk]
+    float2* Qs = reinterpret_cast<float2*>(smem_raw);     // [fa + B - 1][rs]
+    float2* Ts = Qs + (size_t)(a.fa + a.B - 1) * rs;      // [nk][B][nt]
+    float* mags = reinterpret_cast<float*>(Ts + (size_t)a.nk * a.B * a.nt);   // [fa][nk]
 
-    const int tiles_per_ch = (a.n_frames + BD_FA - 1) / BD_FA;
+    const int tiles_per_ch = (a.n_frames + a.fa - 1) / a.fa;
     const int ch = blockIdx.x / tiles_per_ch;
-    const int f0 = (blockIdx.x % tiles_per_ch) * BD_FA;
-    const int nf = min(BD_FA, a.n_frames - f0);
+    const int f0 = (blockIdx.x % tiles_per_ch) * a.fa;
+    const int nf = min(a.fa, a.n_frames - f0);
     const int tid = threadIdx.x;
 
     for (int i = tid; i < a.nk * a.B * a.nt; i += 256) Ts[i] = a.T[i];
@@ -219,8 +220,8 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
         Qs[r * rs + c] = v;
     }
     __syncthreads();
-    for (int it = tid; it < BD_FA * a.nk; it += 256) {
-        const int fl = it % BD_FA, ki = it / BD_FA;
+    for (int it = tid; it < a.fa * a.nk; it += 256) {
+        const int fl = it % a.fa, ki = it / a.fa;
         if (fl >= nf) continue;
         float2 acc = make_float2(0.f, 0.f);
         const float2* tq = Ts + (size_t)ki * a.B * a.nt;
@@ -249,10 +250,16 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
     }
 }
 
-inline size_t blockdft_assemble_smem_bytes(int nk, int nt, int B) {
+inline size_t blockdft_assemble_smem_bytes(int nk, int nt, int B, int fa) {
     const int nc = nk * nt, rs = nc | 1;
-    return (size_t)(BD_FA + B - 1) * rs * sizeof(float2) + (size_t)nk * B * nt * sizeof(float2) +
-           (size_t)BD_FA * nk * sizeof(float) + 16;
+    return (size_t)(fa + B - 1) * rs * sizeof(float2) + (size_t)nk * B * nt * sizeof(float2) +
+           (size_t)fa * nk * sizeof(float) + 16;
+}
+
+inline int blockdft_assemble_frames(int nk, int nt, int B) {
+    int fa = BD_FA_MAX;
+    while (fa > 16 && blockdft_assemble_smem_bytes(nk, nt, B, fa) > 40 * 1024) fa >>= 1;
+    return fa;
 }
 
 }  // namespace o4

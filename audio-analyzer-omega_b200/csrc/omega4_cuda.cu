@@ -16,6 +16,7 @@
 
 #include "bars_kernel.cuh"
 #include "blockdft_kernel.cuh"
+#include "blockdft_tc_kernel.cuh"
 #include "fft_core.cuh"
 #include "kweight_kernel.cuh"
 #include "misc_kernels.cuh"
@@ -258,7 +259,6 @@ struct ResInfo {
     float* tb_frac = nullptr;
     int need_lo = 0, need_cnt = 0;
     Twiddles tw;
-    int sparse = -1;              // index into omega4_plan::sp when the hop-block partial DFT path serves it
 };
 
 // A resolution whose fused output needs only a few FFT bins (blockdft_kernel.cuh)
@@ -267,6 +267,22 @@ struct SparseRes {
     float2* T = nullptr;          // [nk][B][nt]
     float* kw = nullptr;          // [nk]
     int* tb_pos = nullptr;        // [n_tb]
+};
+
+// The resolutions one GEMM over the hop blocks serves, and its constant operand
+struct SparseSet {
+    int n = 0;
+    SparseRes sp[OMEGA4_MAX_RES];
+    int of_res[OMEGA4_MAX_RES];   // index into sp for resolution r, or -1
+    int cols = 0, qs = 0;         // used GEMM columns, Q row stride (padded columns)
+    float* E = nullptr;           // CUDA-core GEMM operand [hop][qs]            (blockdft_kernel.cuh)
+    uint8_t* Eimg = nullptr;      // tensor-core operand images, hi/lo, swizzled  (blockdft_tc_kernel.cuh)
+    int n_halves = 0;
+    SparseSet() { for (int i = 0; i < OMEGA4_MAX_RES; ++i) of_res[i] = -1; }
+    void release() {
+        for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(sp[i].T); cudaFree(sp[i].kw); cudaFree(sp[i].tb_pos); }
+        cudaFree(E); cudaFree(Eimg);
+    }
 };
 
 struct DevBuf {
@@ -300,9 +316,9 @@ struct omega4_plan {
     int kw_nsec = 2, kw_blend = 1, kw_gate = 1;
     double kw_gain = 1.0;
     Twiddles tw_meter;
-    int sp_n = 0, sp_bn = 0;      // sparse resolutions, padded column count of their shared GEMM
-    SparseRes sp[OMEGA4_MAX_RES];
-    float* sp_E = nullptr;        // [hop][sp_bn]
+    SparseSet set_cc;             // fp32 CUDA-core GEMM: up to 128 columns
+    SparseSet set_tc;             // 3xTF32 tcgen05 GEMM: up to 512 columns
+    bool tensor_default = true;   // OMEGA4_TENSOR=0 makes the CUDA-core GEMM the default
     DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32;
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
     // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
@@ -366,6 +382,145 @@ static size_t boff_of(const omega4_plan_desc* d, int r) {
     size_t o = 0;
     for (int i = 0; i < r; ++i) o += (size_t)d->fft_sizes[i] / 2 + 1;
     return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// hop-block partial DFT tables (blockdft_kernel.cuh / blockdft_tc_kernel.cuh)
+// ------------------------------------------------------------------------------------------
+static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std::vector<std::vector<int>>& idx,
+                            const std::vector<std::vector<int>>& lo, bool tensor, SparseSet* set) {
+    const int H = d->hop;
+    if ((H % (tensor ? TC_KC : BD_KC)) != 0) return OMEGA4_OK;
+    const int max_cols = tensor ? 2 * TC_BN : 128;
+    int order[OMEGA4_MAX_RES];
+    for (int r = 0; r < d->n_res; ++r) order[r] = r;
+    for (int i = 0; i < d->n_res; ++i)                 // largest transform first
+        for (int j = i + 1; j < d->n_res; ++j)
+            if (p->res[order[j]].n > p->res[order[i]].n) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+    std::vector<std::vector<float>> ecols;             // per accepted resolution: [hop][2 nk nt]
+    int cols = 0;
+    size_t woff2[OMEGA4_MAX_RES];
+    { size_t o = 0; for (int r = 0; r < d->n_res; ++r) { woff2[r] = o; o += d->fft_sizes[r]; } }
+    for (int oi = 0; oi < d->n_res; ++oi) {
+        const int r = order[oi];
+        const ResInfo& ri = p->res[r];
+        const int N = ri.n;
+        if (N % H != 0 || N / H < 2 || N / H > 64) continue;
+        std::vector<int> bins;
+        for (int l : lo[r]) if (l >= 0) { bins.push_back(l); bins.push_back(l + 1); }
+        std::sort(bins.begin(), bins.end());
+        bins.erase(std::unique(bins.begin(), bins.end()), bins.end());
+        if (bins.empty()) continue;
+        // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
+        const float* w = d->windows + woff2[r];
+        const double phi = 6.283185307179586476925287 / (double)(N - 1);
+        double G[3][4] = {{0}};
+        for (int i = 0; i < N; ++i) {
+            const double c[3] = {1.0, cos(phi * i), cos(2.0 * phi * i)};
+            for (int u = 0; u < 3; ++u) { for (int v = 0; v < 3; ++v) G[u][v] += c[u] * c[v]; G[u][3] += c[u] * (double)w[i]; }
+        }
+        bool singular = false;
+        for (int u = 0; u < 3 && !singular; ++u) {        // Gauss-Jordan with partial pivoting
+            int piv = u;
+            for (int v = u + 1; v < 3; ++v) if (fabs(G[v][u]) > fabs(G[piv][u])) piv = v;
+            if (fabs(G[piv][u]) < 1e-9) { singular = true; break; }
+            if (piv != u) for (int c2 = 0; c2 < 4; ++c2) { double t = G[u][c2]; G[u][c2] = G[piv][c2]; G[piv][c2] = t; }
+            for (int v = 0; v < 3; ++v) {
+                if (v == u) continue;
+                const double f = G[v][u] / G[u][u];
+                for (int c2 = 0; c2 < 4; ++c2) G[v][c2] -= f * G[u][c2];
+            }
+        }
+        if (singular) continue;
+        double am[3] = {G[0][3] / G[0][0], G[1][3] / G[1][1], G[2][3] / G[2][2]};
+        double resid = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double fit = am[0] + am[1] * cos(phi * i) + am[2] * cos(2.0 * phi * i);
+            resid = fmax(resid, fabs(fit - (double)w[i]));
+        }
+        if (resid > 1.5e-7) continue;                     // not a cosine-sum window: keep the FFT path
+        int tm[5]; double tc[5]; int nt = 0;
+        tm[nt] = 0; tc[nt] = am[0]; ++nt;
+        for (int m = 1; m <= 2; ++m)
+            if (fabs(am[m]) > 1e-9) { tm[nt] = m; tc[nt] = 0.5 * am[m]; ++nt; tm[nt] = -m; tc[nt] = 0.5 * am[m]; ++nt; }
+        const int nk = (int)bins.size();
+        const int rc_cols = 2 * nk * nt;
+        // cost model against the FFT kernel's ~2.5 N log2 N instructions per frame (measured ~22 T instr/s):
+        //   CUDA-core GEMM: cols x hop FMAs at ~23 T/s  -> accept below half the FFT's count
+        //   tensor-core GEMM: 3 x cols x hop MACs at ~250 T/s (measured, 3xTF32)
+        const double fft_cost = 2.5 * N * (ri.log2m + 1);
+        if (!tensor && (double)rc_cols * H * 2.0 > fft_cost) continue;
+        if (tensor && (double)rc_cols * H > 6.6 * fft_cost) continue;
+        if (cols + rc_cols > max_cols) continue;
+        SparseRes& sp = set->sp[set->n];
+        sp.r = r; sp.nk = nk; sp.nt = nt; sp.B = N / H; sp.col0 = cols;
+        std::vector<float> ec((size_t)H * rc_cols);
+        std::vector<float2> T((size_t)nk * sp.B * nt);
+        std::vector<float> kw(nk);
+        const double two_pi = 6.283185307179586476925287;
+        for (int ki = 0; ki < nk; ++ki) {
+            kw[ki] = d->bin_weights ? d->bin_weights[boff_of(d, r) + bins[ki]] : 1.f;
+            for (int t = 0; t < nt; ++t) {
+                const double th = tm[t] * phi - two_pi * (double)bins[ki] / (double)N;
+                for (int n2 = 0; n2 < H; ++n2) {
+                    const double ang = fmod(th * n2, two_pi);
+                    ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t)] = (float)cos(ang);
+                    ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t) + 1] = (float)sin(ang);
+                }
+                for (int b = 0; b < sp.B; ++b) {
+                    const double ang = fmod(th * (double)H * b, two_pi);
+                    T[((size_t)ki * sp.B + b) * nt + t] = make_float2((float)(tc[t] * cos(ang)), (float)(tc[t] * sin(ang)));
+                }
+            }
+        }
+        std::vector<int> pos(idx[r].size(), -1);
+        for (size_t j = 0; j < lo[r].size(); ++j)
+            if (lo[r][j] >= 0) pos[j] = (int)(std::lower_bound(bins.begin(), bins.end(), lo[r][j]) - bins.begin());
+        int rc = upload((void**)&sp.T, T.data(), T.size() * sizeof(float2)); if (rc) return rc;
+        rc = upload((void**)&sp.kw, kw.data(), kw.size() * sizeof(float)); if (rc) return rc;
+        rc = upload((void**)&sp.tb_pos, pos.data(), pos.size() * sizeof(int)); if (rc) return rc;
+        set->of_res[r] = set->n++;
+        ecols.push_back(std::move(ec));
+        cols += rc_cols;
+    }
+    if (set->n == 0) return OMEGA4_OK;
+    set->cols = cols;
+    if (!tensor) {
+        set->qs = cols <= 32 ? 32 : (cols <= 64 ? 64 : 128);
+        std::vector<float> E((size_t)H * set->qs, 0.f);
+        for (int si = 0; si < set->n; ++si) {
+            const SparseRes& sp = set->sp[si];
+            const int rc_cols = 2 * sp.nk * sp.nt;
+            for (int n2 = 0; n2 < H; ++n2)
+                memcpy(&E[(size_t)n2 * set->qs + sp.col0], &ecols[si][(size_t)n2 * rc_cols], rc_cols * sizeof(float));
+        }
+        return upload((void**)&set->E, E.data(), E.size() * sizeof(float));
+    }
+    // tensor-core operand: per column half and K chunk, the (hi, lo) TF32 split of E^T as byte images of
+    // the K-major SWIZZLE_64B shared-memory layout
+    set->n_halves = cols <= TC_BN ? 1 : 2;
+    set->qs = set->n_halves * TC_BN;
+    const int nkc = H / TC_KC;
+    std::vector<uint8_t> img((size_t)set->n_halves * nkc * 2 * TC_B_BYTES, 0);
+    for (int si = 0; si < set->n; ++si) {
+        const SparseRes& sp = set->sp[si];
+        const int rc_cols = 2 * sp.nk * sp.nt;
+        for (int cc = 0; cc < rc_cols; ++cc) {
+            const int col = sp.col0 + cc, h = col / TC_BN, n = col % TC_BN;
+            for (int k = 0; k < H; ++k) {
+                const float v = ecols[si][(size_t)k * rc_cols + cc];
+                uint32_t bits; memcpy(&bits, &v, 4); bits &= 0xFFFFE000u;
+                float hi; memcpy(&hi, &bits, 4);
+                const float lo2 = v - hi;
+                const int kc = k / TC_KC, e = k % TC_KC;
+                const size_t base = ((size_t)(h * nkc + kc) * 2) * TC_B_BYTES;
+                const int off = tc_sw64_offset(n, e >> 2) + (e & 3) * 4;
+                memcpy(&img[base + off], &hi, 4);
+                memcpy(&img[base + TC_B_BYTES + off], &lo2, 4);
+            }
+        }
+    }
+    return upload((void**)&set->Eimg, img.data(), img.size());
 }
 
 static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
@@ -435,107 +590,11 @@ static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
         rc = upload((void**)&ri.tb_lo, lo[r].data(), lo[r].size() * sizeof(int)); if (rc) return rc;
         rc = upload((void**)&ri.tb_frac, fr[r].data(), fr[r].size() * sizeof(float)); if (rc) return rc;
     }
-    // hop-block partial DFT path (blockdft_kernel.cuh) for resolutions whose combine segments read
-    // only a few FFT bins and whose window is a short cosine sum
-    if (p->disjoint && (d->hop % BD_KC) == 0) {
-        int order[OMEGA4_MAX_RES];
-        for (int r = 0; r < d->n_res; ++r) order[r] = r;
-        for (int i = 0; i < d->n_res; ++i)                 // largest transform first
-            for (int j = i + 1; j < d->n_res; ++j)
-                if (p->res[order[j]].n > p->res[order[i]].n) { int t = order[i]; order[i] = order[j]; order[j] = t; }
-        std::vector<std::vector<float>> ecols;             // per accepted resolution: [hop][2 nk nt]
-        int cols = 0;
-        size_t woff2[OMEGA4_MAX_RES];
-        { size_t o = 0; for (int r = 0; r < d->n_res; ++r) { woff2[r] = o; o += d->fft_sizes[r]; } }
-        for (int oi = 0; oi < d->n_res; ++oi) {
-            const int r = order[oi];
-            ResInfo& ri = p->res[r];
-            const int N = ri.n, H = d->hop;
-            if (N % H != 0 || N / H < 2 || N / H > 64) continue;
-            std::vector<int> bins;
-            for (int l : lo[r]) if (l >= 0) { bins.push_back(l); bins.push_back(l + 1); }
-            std::sort(bins.begin(), bins.end());
-            bins.erase(std::unique(bins.begin(), bins.end()), bins.end());
-            if (bins.empty()) continue;
-            // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
-            const float* w = d->windows + woff2[r];
-            const double phi = 6.283185307179586476925287 / (double)(N - 1);
-            double G[3][4] = {{0}};
-            for (int i = 0; i < N; ++i) {
-                const double c[3] = {1.0, cos(phi * i), cos(2.0 * phi * i)};
-                for (int u = 0; u < 3; ++u) { for (int v = 0; v < 3; ++v) G[u][v] += c[u] * c[v]; G[u][3] += c[u] * (double)w[i]; }
-            }
-            bool singular = false;
-            for (int u = 0; u < 3 && !singular; ++u) {        // Gauss-Jordan with partial pivoting
-                int piv = u;
-                for (int v = u + 1; v < 3; ++v) if (fabs(G[v][u]) > fabs(G[piv][u])) piv = v;
-                if (fabs(G[piv][u]) < 1e-9) { singular = true; break; }
-                if (piv != u) for (int c2 = 0; c2 < 4; ++c2) { double t = G[u][c2]; G[u][c2] = G[piv][c2]; G[piv][c2] = t; }
-                for (int v = 0; v < 3; ++v) {
-                    if (v == u) continue;
-                    const double f = G[v][u] / G[u][u];
-                    for (int c2 = 0; c2 < 4; ++c2) G[v][c2] -= f * G[u][c2];
-                }
-            }
-            if (singular) continue;
-            double am[3] = {G[0][3] / G[0][0], G[1][3] / G[1][1], G[2][3] / G[2][2]};
-            double resid = 0.0;
-            for (int i = 0; i < N; ++i) {
-                const double fit = am[0] + am[1] * cos(phi * i) + am[2] * cos(2.0 * phi * i);
-                resid = fmax(resid, fabs(fit - (double)w[i]));
-            }
-            if (resid > 1.5e-7) continue;                     // not a cosine-sum window: keep the FFT path
-            int tm[5]; double tc[5]; int nt = 0;
-            tm[nt] = 0; tc[nt] = am[0]; ++nt;
-            for (int m = 1; m <= 2; ++m)
-                if (fabs(am[m]) > 1e-9) { tm[nt] = m; tc[nt] = 0.5 * am[m]; ++nt; tm[nt] = -m; tc[nt] = 0.5 * am[m]; ++nt; }
-            const int nk = (int)bins.size();
-            const int rc_cols = 2 * nk * nt;
-            // GEMM FMAs per hop must be well below the FFT's ~2.5 N log2 N instructions
-            if ((double)rc_cols * H * 2.0 > 2.5 * N * (ri.log2m + 1)) continue;
-            if (cols + rc_cols > 128) continue;
-            SparseRes& sp = p->sp[p->sp_n];
-            sp.r = r; sp.nk = nk; sp.nt = nt; sp.B = N / H; sp.col0 = cols;
-            std::vector<float> ec((size_t)H * rc_cols);
-            std::vector<float2> T((size_t)nk * sp.B * nt);
-            std::vector<float> kw(nk);
-            const double two_pi = 6.283185307179586476925287;
-            for (int ki = 0; ki < nk; ++ki) {
-                kw[ki] = d->bin_weights ? d->bin_weights[boff_of(d, r) + bins[ki]] : 1.f;
-                for (int t = 0; t < nt; ++t) {
-                    const double th = tm[t] * phi - two_pi * (double)bins[ki] / (double)N;
-                    for (int n2 = 0; n2 < H; ++n2) {
-                        const double ang = fmod(th * n2, two_pi);
-                        ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t)] = (float)cos(ang);
-                        ec[(size_t)n2 * rc_cols + 2 * (ki * nt + t) + 1] = (float)sin(ang);
-                    }
-                    for (int b = 0; b < sp.B; ++b) {
-                        const double ang = fmod(th * (double)H * b, two_pi);
-                        T[((size_t)ki * sp.B + b) * nt + t] = make_float2((float)(tc[t] * cos(ang)), (float)(tc[t] * sin(ang)));
-                    }
-                }
-            }
-            std::vector<int> pos(idx[r].size(), -1);
-            for (size_t j = 0; j < lo[r].size(); ++j)
-                if (lo[r][j] >= 0) pos[j] = (int)(std::lower_bound(bins.begin(), bins.end(), lo[r][j]) - bins.begin());
-            int rc = upload((void**)&sp.T, T.data(), T.size() * sizeof(float2)); if (rc) return rc;
-            rc = upload((void**)&sp.kw, kw.data(), kw.size() * sizeof(float)); if (rc) return rc;
-            rc = upload((void**)&sp.tb_pos, pos.data(), pos.size() * sizeof(int)); if (rc) return rc;
-            ri.sparse = p->sp_n++;
-            ecols.push_back(std::move(ec));
-            cols += rc_cols;
-        }
-        if (p->sp_n > 0) {
-            p->sp_bn = cols <= 32 ? 32 : (cols <= 64 ? 64 : 128);
-            std::vector<float> E((size_t)d->hop * p->sp_bn, 0.f);
-            for (int si = 0; si < p->sp_n; ++si) {
-                const SparseRes& sp = p->sp[si];
-                const int rc_cols = 2 * sp.nk * sp.nt;
-                for (int n2 = 0; n2 < d->hop; ++n2)
-                    memcpy(&E[(size_t)n2 * p->sp_bn + sp.col0], &ecols[si][(size_t)n2 * rc_cols], rc_cols * sizeof(float));
-            }
-            int rc = upload((void**)&p->sp_E, E.data(), E.size() * sizeof(float)); if (rc) return rc;
-        }
+    // hop-block partial DFT path for resolutions whose combine segments read only a few FFT bins and
+    // whose window is a short cosine sum: one set for the fp32 CUDA-core GEMM, one for the tensor cores
+    if (p->disjoint) {
+        int rc = build_sparse_set(p, d, idx, lo, false, &p->set_cc); if (rc) return rc;
+        rc = build_sparse_set(p, d, idx, lo, true, &p->set_tc); if (rc) return rc;
     }
     // meters
     int rc = upload((void**)&p->hann64, d->meter_hann, (size_t)p->W * sizeof(double)); if (rc) return rc;
@@ -561,6 +620,7 @@ extern "C" omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int dev
     if (cudaSetDevice(device) != cudaSuccess) { fail(OMEGA4_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
     omega4_plan* p = new omega4_plan();
     p->device = device;
+    if (const char* e = getenv("OMEGA4_TENSOR")) p->tensor_default = atoi(e) != 0;
     if (const char* e = getenv("OMEGA4_HOST_CHUNK_MB")) {           // tuning knob of the host-buffer pipeline
         long mb = atol(e);
         if (mb >= 16 && mb <= 16384) p->host_chunk_bytes = (size_t)mb << 20;
@@ -580,8 +640,7 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
     cudaFree(p->hann64); cudaFree(p->hann32);
     p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
-    for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(p->sp[i].T); cudaFree(p->sp[i].kw); cudaFree(p->sp[i].tb_pos); }
-    cudaFree(p->sp_E);
+    p->set_cc.release(); p->set_tc.release();
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
     for (auto& sl : p->slots) {
@@ -756,8 +815,10 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     int first[OMEGA4_MAX_RES];
     bool use_sparse[OMEGA4_MAX_RES] = {false};
     bool any_sparse = false;
+    const bool tensor = p->set_tc.n > 0 && (p->tensor_default ? !(flags & OMEGA4_FLAG_NO_TENSOR) : (flags & OMEGA4_FLAG_TENSOR) != 0);
+    const SparseSet& set = tensor ? p->set_tc : p->set_cc;
     for (int r = 0; r < p->n_res; ++r) {
-        use_sparse[r] = combined && fused && p->res[r].sparse >= 0 && !(mags && mags[r]) &&
+        use_sparse[r] = combined && fused && set.of_res[r] >= 0 && !(mags && mags[r]) &&
                         !(flags & OMEGA4_FLAG_NO_BLOCKDFT);
         any_sparse = any_sparse || use_sparse[r];
     }
@@ -795,35 +856,50 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         // one GEMM over the hop blocks serves every sparse resolution; then one assembly per resolution
         int j0 = 1 << 30;
         for (int r = 0; r < p->n_res; ++r)
-            if (use_sparse[r]) { const int j = first[r] + 1 - p->sp[p->res[r].sparse].B; if (j < j0) j0 = j; }
+            if (use_sparse[r]) { const int j = first[r] + 1 - set.sp[set.of_res[r]].B; if (j < j0) j0 = j; }
         const int nb = n_hops - j0;
         const float* Q = nullptr;
         if (nb > 0) {
-            int rc = qbuf->ensure((size_t)n_ch * nb * p->sp_bn * sizeof(float));
+            int rc = qbuf->ensure((size_t)n_ch * nb * set.qs * sizeof(float));
             if (rc) return rc;
-            BlockDftGemmArgs g;
-            memset(&g, 0, sizeof g);
-            g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
-            g.E = p->sp_E; g.Q = (float*)qbuf->p;
-            Q = g.Q;
-            Bracket b(p, s, timing, "blockdft_gemm");
-            rc = launch_blockdft_gemm(p->sp_bn, g, s);
-            if (rc) return rc;
+            Q = (float*)qbuf->p;
+            if (tensor) {
+                BlockDftTcArgs g;
+                memset(&g, 0, sizeof g);
+                g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
+                g.n_halves = set.n_halves; g.Eimg = set.Eimg; g.Q = (float*)qbuf->p; g.qs = set.qs;
+                const size_t smem = blockdft_tc_smem_bytes();
+                CK(cudaFuncSetAttribute(blockdft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const long long grid = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
+                if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
+                Bracket b(p, s, timing, "blockdft_tc_gemm");
+                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, s>>>(g);
+                CK(cudaGetLastError());
+            } else {
+                BlockDftGemmArgs g;
+                memset(&g, 0, sizeof g);
+                g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
+                g.E = set.E; g.Q = (float*)qbuf->p;
+                Bracket b(p, s, timing, "blockdft_gemm");
+                rc = launch_blockdft_gemm(set.qs, g, s);
+                if (rc) return rc;
+            }
         }
         for (int r = 0; r < p->n_res; ++r) {
             if (!use_sparse[r]) continue;
             const ResInfo& ri = p->res[r];
-            const SparseRes& sp = p->sp[ri.sparse];
+            const SparseRes& sp = set.sp[set.of_res[r]];
             BlockDftAsmArgs a;
             memset(&a, 0, sizeof a);
-            a.Q = Q; a.qs = p->sp_bn; a.col0 = sp.col0; a.nb = nb > 0 ? nb : 0; a.j0 = j0;
+            a.Q = Q; a.qs = set.qs; a.col0 = sp.col0; a.nb = nb > 0 ? nb : 0; a.j0 = j0;
             a.nk = sp.nk; a.nt = sp.nt; a.B = sp.B; a.T = sp.T; a.kw = sp.kw;
             a.n_ch = n_ch; a.n_frames = n_hops; a.first_frame = first[r];
             a.comb_out = combined; a.Tbins = p->T; a.n_tb = ri.n_tb; a.tb_idx = ri.tb_idx; a.tb_pos = sp.tb_pos;
             a.tb_frac = ri.tb_frac; a.wnum = ri.weight; a.wden = ri.weight;
-            const size_t smem = blockdft_assemble_smem_bytes(sp.nk, sp.nt, sp.B);
+            a.fa = blockdft_assemble_frames(sp.nk, sp.nt, sp.B);
+            const size_t smem = blockdft_assemble_smem_bytes(sp.nk, sp.nt, sp.B, a.fa);
             CK(cudaFuncSetAttribute(blockdft_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const long long grid = (long long)((n_hops + BD_FA - 1) / BD_FA) * n_ch;
+            const long long grid = (long long)((n_hops + a.fa - 1) / a.fa) * n_ch;
             if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft assemble grid too large");
             char name[32];
             snprintf(name, sizeof name, "blockdft_asm_%d", ri.n);
@@ -890,7 +966,10 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
     const long long dstride = (hist_al + new_len + 3) / 4 * 4;
     size_t per_ch = (size_t)dstride * sizeof(float) + (size_t)n_hops * 2 * sizeof(double) + ST_STATE * sizeof(double);
     if (combined) per_ch += (size_t)n_hops * p->T * sizeof(float);
-    if (combined && p->sp_n > 0) per_ch += (size_t)(n_hops + 64) * p->sp_bn * sizeof(float);
+    {
+        const int qs = p->set_tc.qs > p->set_cc.qs ? p->set_tc.qs : p->set_cc.qs;
+        if (combined && qs > 0) per_ch += (size_t)(n_hops + 64) * qs * sizeof(float);
+    }
     if (meters) per_ch += (size_t)n_hops * 5 * sizeof(float);
     bool want_mag[OMEGA4_MAX_RES] = {false};
     for (int r = 0; r < p->n_res; ++r) {

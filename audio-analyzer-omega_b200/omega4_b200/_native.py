@@ -26,6 +26,8 @@ FLAG_TIME_KERNELS = 1
 FLAG_FRESH_METERS = 2
 FLAG_CONCURRENT_METERS = 4
 FLAG_NO_BLOCKDFT = 8
+FLAG_NO_TENSOR = 16
+FLAG_TENSOR = 32
 ABI_VERSION = 1
 
 #: every symbol include/omega4_cuda.h declares (checked by tests/test_abi_symbols.py)

@@ -49,6 +49,10 @@ extern "C" {
 #define OMEGA4_FLAG_NO_BLOCKDFT 8                /* evaluate every resolution with the full FFT kernel even where the fused
                                                     output needs only a few bins (default: hop-block partial DFT there) */
 
+#define OMEGA4_FLAG_NO_TENSOR 16                 /* run the hop-block partial DFT GEMM on the CUDA cores (fp32 FFMA) instead
+                                                    of the tensor cores (tcgen05 kind::tf32, 3xTF32 split precision) */
+#define OMEGA4_FLAG_TENSOR 32                    /* force the tensor-core GEMM when the plan default is off (OMEGA4_TENSOR=0) */
+
 typedef struct omega4_plan omega4_plan;
 
 /* Everything that defines the reference's behaviour is DATA computed on the host with the

@@ -171,25 +171,55 @@ def _kernel_names(plan):
 
 
 def test_blockdft_path_matches_golden_and_full_fft(plan, golden):
-    """Fused output only (no magnitudes): N = 8192 feeds 5 target bins from 10 FFT bins, so the
-    library evaluates it as hop-block partial DFTs (blockdft_kernel.cuh).  Same golden vectors, and
-    the full-FFT evaluation of the same call (OMEGA4_FLAG_NO_BLOCKDFT) must agree."""
+    """Fused output only (no magnitudes): N = 8192 feeds 5 target bins from 10 FFT bins and N = 4096
+    feeds 20 from 40, so the library evaluates them as hop-block partial DFTs -- by default as one
+    3xTF32 tcgen05 GEMM (blockdft_tc_kernel.cuh), with OMEGA4_FLAG_NO_TENSOR as the fp32 CUDA-core GEMM
+    for the 8192 alone (blockdft_kernel.cuh).  Same golden vectors; the full-FFT evaluation of the same
+    call (OMEGA4_FLAG_NO_BLOCKDFT) must agree."""
     from omega4_b200 import _native as N
     g = golden("multires_baseline.npz")
-    out = plan.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
-    names = _kernel_names(plan)
-    assert "blockdft_gemm" in names and "blockdft_asm_8192" in names and "multires_fft_8192" not in names
-    assert "multires_fft_4096" in names
-    comb = out["combined"][0]
-    assert np.array_equal(comb == 0, g["combined"] == 0)
-    assert_spectrum_close(comb, g["combined"], TOL_DB, label="blockdft combined")
     full = plan.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | N.FLAG_NO_BLOCKDFT)
     names = _kernel_names(plan)
-    assert "multires_fft_8192" in names and "blockdft_gemm" not in names
-    assert np.array_equal(full["combined"][0] == 0, comb == 0)
-    scale = full["combined"][0].max(axis=1, keepdims=True) + 1e-20
-    assert (np.abs(full["combined"][0] - comb) / scale).max() < 2e-6
-    assert np.array_equal(full["combined"][0][:, 6:], comb[:, 6:])      # other resolutions untouched
+    assert "multires_fft_8192" in names and not any(n.startswith("blockdft") for n in names)
+    fullc = full["combined"][0]
+    scale = fullc.max(axis=1, keepdims=True) + 1e-20
+    for flags, want, absent in ((0, ("blockdft_tc_gemm", "blockdft_asm_8192", "blockdft_asm_4096"),
+                                 ("multires_fft_8192", "multires_fft_4096", "blockdft_gemm")),
+                                (N.FLAG_NO_TENSOR, ("blockdft_gemm", "blockdft_asm_8192", "multires_fft_4096"),
+                                 ("multires_fft_8192", "blockdft_tc_gemm", "blockdft_asm_4096"))):
+        out = plan.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | flags)
+        names = _kernel_names(plan)
+        assert all(w in names for w in want) and not any(a in names for a in absent), names
+        comb = out["combined"][0]
+        assert np.array_equal(comb == 0, g["combined"] == 0)
+        assert_spectrum_close(comb, g["combined"], TOL_DB, label=f"blockdft flags={flags}")
+        assert np.array_equal(fullc == 0, comb == 0)
+        assert (np.abs(fullc - comb) / scale).max() < (2e-6 if flags else 2e-5)
+        assert np.array_equal(fullc[:, 26:], comb[:, 26:])                  # 2048 / 1024 resolutions untouched
+
+
+def test_blockdft_strong_tone_next_to_weak_content():
+    """Worst case for the split-precision tensor-core GEMM: a full-scale 1 kHz tone leaking into the
+    sparse low bins, which hold a tone 50 dB below it; float64 reference."""
+    from omega4_b200 import _native as N
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
+    n = 40 * HOP
+    t = np.arange(n) / 48000.0
+    x = (0.9 * np.sin(2 * np.pi * 1000.0 * t) + 0.9 * 10 ** (-50 / 20) * np.sin(2 * np.pi * 97.0 * t + 0.3)).astype(np.float32)
+    mr = O.OracleMultiResFFT(48000, 20000, list(O.BASELINE_CONFIGS))
+    for k in range(40):
+        res = mr.process_audio_chunk(x[k * HOP:(k + 1) * HOP])
+    # float64 evaluation of the same last frame
+    ref64 = {}
+    for i, c in enumerate(mr.configs):
+        fr = x[n - c.fft_size:].astype(np.float64) * mr.windows[i].astype(np.float64)
+        ref64[i] = (np.abs(np.fft.rfft(fr)) * mr.bin_weights(i)).astype(np.float64)
+    want = mr.combine({i: v.astype(np.float32) for i, v in ref64.items()}, 512)[0]
+    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
+    for flags in (0, N.FLAG_NO_TENSOR, N.FLAG_NO_BLOCKDFT):
+        got = p.analyze_host(x[None, :], want_meters=False, flags=flags)["combined"][0, 39]
+        assert_spectrum_close(got, want, TOL_DB, label=f"strong tone flags={flags}")
+    p.close()
 
 
 def test_blockdft_96k_default_and_window_variants(golden):
@@ -203,6 +233,7 @@ def test_blockdft_96k_default_and_window_variants(golden):
     out = p.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
     names = _kernel_names(p)
     assert "blockdft_asm_32768" in names and "blockdft_asm_16384" in names and "multires_fft_32768" not in names
+    assert "blockdft_tc_gemm" in names
     assert_spectrum_close(out["combined"][0, 60:], g["combined_tail"], TOL_DB, label="96k blockdft")
     assert np.array_equal(out["combined"][0, 60:] == 0, g["combined_tail"] == 0)
     p.close()
@@ -211,7 +242,7 @@ def test_blockdft_96k_default_and_window_variants(golden):
     g = golden("multires_default.npz")
     p = AnalysisPlan(48000, DEFAULT_CONFIGS, 1024)
     out = p.analyze_host(g["x"][None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
-    assert "blockdft_gemm" not in _kernel_names(p)
+    assert "blockdft_gemm" not in _kernel_names(p) and "blockdft_tc_gemm" in _kernel_names(p)   # 200 columns: tensor cores only
     assert np.array_equal(out["combined"][0] == 0, g["combined"] == 0)
     assert_spectrum_close(out["combined"][0], g["combined"], TOL_DB, label="default blockdft")
     p.close()
@@ -221,9 +252,10 @@ def test_blockdft_96k_default_and_window_variants(golden):
     cfg = [(c[0], c[1], c[2], c[3], wt) for c, wt in zip(BASELINE_CONFIGS, wts)]
     x = golden("multires_baseline.npz")["x"][: int(g["n_samples"])]
     p = AnalysisPlan(48000, cfg, 512)
-    out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
-    assert "blockdft_gemm" in _kernel_names(p)
-    assert_spectrum_close(out["combined"][0, 23], g["combined_h23"], TOL_DB, label="window variants blockdft")
+    for fl in (0, N.FLAG_NO_TENSOR):
+        out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | fl)
+        assert ("blockdft_gemm" if fl else "blockdft_tc_gemm") in _kernel_names(p)
+        assert_spectrum_close(out["combined"][0, 23], g["combined_h23"], TOL_DB, label="window variants blockdft")
     p.close()
     # a window that is NOT a cosine sum keeps the FFT path
     rng = np.random.default_rng(5)
@@ -231,7 +263,7 @@ def test_blockdft_96k_default_and_window_variants(golden):
     wins[0] = (wins[0] * (1 + 0.01 * rng.standard_normal(8192))).astype(np.float32)
     p = AnalysisPlan(48000, BASELINE_CONFIGS, 512, windows=wins)
     out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
-    assert "blockdft_gemm" not in _kernel_names(p) and "multires_fft_8192" in _kernel_names(p)
+    assert not any(n.startswith("blockdft") and "8192" in n for n in _kernel_names(p)) and "multires_fft_8192" in _kernel_names(p)
     mr = O.OracleMultiResFFT(48000, 20000, list(O.BASELINE_CONFIGS))
     mr.windows[0] = wins[0]
     for k in range(24):
