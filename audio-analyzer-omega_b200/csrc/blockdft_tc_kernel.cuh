@@ -149,14 +149,24 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) nxt[q] = __ldg(a_src[q]);
 
+    // B operand of chunk 0; afterwards iteration kc requests chunk kc + 1, one full iteration ahead
+    if (tid == 0) {
+        tc_mbar_expect_tx(bar_b, 2 * TC_B_BYTES);
+        tc_bulk_g2s(tiles + 2 * TC_A_BYTES, eimg, 2 * TC_B_BYTES, bar_b);
+    }
     for (int kc = 0; kc < n_kc; ++kc) {
         const int s = kc % TC_STAGES;
         const uint32_t use = (uint32_t)(kc / TC_STAGES);
         uint8_t* st = tiles + s * TC_STAGE_BYTES;
-        if (kc >= TC_STAGES) tc_mbar_wait(bar_m + s, (use - 1) & 1);     // MMAs that read this stage have retired
-        if (tid == 0) {
-            tc_mbar_expect_tx(bar_b + s, 2 * TC_B_BYTES);
-            tc_bulk_g2s(st + 2 * TC_A_BYTES, eimg + (size_t)kc * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + s);
+        // stage (kc+1) % STAGES was last read by the MMAs of chunk kc - 2: once those have retired
+        // (a commit covers every earlier MMA, so chunk kc - 3's stage -- ours -- is free as well) the next
+        // B chunk can be requested and this chunk's A tiles written
+        if (kc >= 2) tc_mbar_wait(bar_m + (kc - 2) % TC_STAGES, (uint32_t)((kc - 2) / TC_STAGES) & 1);
+        if (tid == 0 && kc + 1 < n_kc) {
+            const int s1 = (kc + 1) % TC_STAGES;
+            tc_mbar_expect_tx(bar_b + s1, 2 * TC_B_BYTES);
+            tc_bulk_g2s(tiles + s1 * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)(kc + 1) * 2 * TC_B_BYTES,
+                        2 * TC_B_BYTES, bar_b + s1);
         }
         float4 cur[4];
 #pragma unroll

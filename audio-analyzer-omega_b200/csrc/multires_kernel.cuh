@@ -151,13 +151,15 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
     const int tile = blockIdx.x % tiles_per_ch;
     const int f0 = tile * frames_per_cta;
 
-    // per-thread constants: window pairs for the 16 owned inputs, stage twiddles
-    float2 win[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-        win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
-    LocalTw<LOG2M> st;
-    load_local_twiddles<LOG2M>(st, a.twM, t);
+    // per-thread constants: all 2 x 15 stage twiddles in registers; the window pairs of the 16 owned
+    // inputs are re-read from L1 every round (16 loads instead of 88 twiddle-product instructions)
+    LocalTwFull<LOG2M> st;
+    {
+        LocalTw<LOG2M> st4;
+        load_local_twiddles<LOG2M>(st4, a.twM, t);
+        expand_local_twiddles<LOG2M>(st4, st);
+    }
+    const float2* wptr = reinterpret_cast<const float2*>(a.window) + t;
 
     const float* xch = a.x + (long long)ch * a.ch_stride + a.frame_off0;
     float2 v[16];
@@ -174,9 +176,9 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
         const int f = f0 + r * CONC + g;
         const bool valid = f < a.n_frames;
         const bool active = valid && f >= a.first_frame;
-        if (active) {
+        if (active && a.window) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j].x *= win[j].x; v[j].y *= win[j].y; }
+            for (int j = 0; j < 16; ++j) { const float2 w = __ldg(wptr + j * TPF); v[j].x *= w.x; v[j].y *= w.y; }
         }
         // the combine of the previous round runs right after this round's first barrier, which
         // also publishes the previous epilogue's magnitudes

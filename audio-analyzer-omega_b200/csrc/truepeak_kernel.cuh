@@ -59,12 +59,14 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
     const int tile = blockIdx.x % tiles_per_ch;
     const int f0 = tile * frames_per_cta;
 
-    float2 win[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-        win[j] = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
-    LocalTw<LOG2M> st;
-    load_local_twiddles<LOG2M>(st, a.twM, t);
+    // all 2 x 15 stage twiddles live in registers (four transforms per frame reuse them); the window is
+    // re-read from L1 once per frame instead
+    LocalTwFull<LOG2M> st;
+    {
+        LocalTw<LOG2M> st4;
+        load_local_twiddles<LOG2M>(st4, a.twM, t);
+        expand_local_twiddles<LOG2M>(st4, st);
+    }
     const float inv_m = 1.0f / (float)M;
     auto nop = []() {};
 
@@ -86,7 +88,8 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                v[j].x *= win[j].x; v[j].y *= win[j].y;
+                const float2 w = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
+                v[j].x *= w.x; v[j].y *= w.y;
                 pk = fmaxf(pk, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
             }
         }

@@ -217,6 +217,29 @@ def main():
     allrows = gather_rows(rows, n_streams * world) if world > 1 else rows
     checksum = float(allrows.double().sum())
 
+    # ---------------- SURVEY section 8f rows, timed separately (not part of the headline metric)
+    next_rows = {}
+    try:
+        from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+        post = SpectrumPostProcessor(T_BINS, SR, 2048, device=local)
+        post._ensure()
+        bars = torch.empty((n_ch, n_hops, post.n_valid), dtype=torch.float32, device=dev)
+        post.process_device(comb, bars)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        post.process_device(comb, bars)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        next_rows["app_post_processing"] = {"ms": ms, "bars_per_frame": post.n_valid,
+                                            "gbs": (comb.numel() + bars.numel()) * 4 / (ms / 1e3) / 1e9,
+                                            "frac_hbm": (comb.numel() + bars.numel()) * 4 / (ms / 1e3) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0))}
+        del bars
+        post.close()
+    except Exception as e:                       # never let an auxiliary row break the headline line
+        next_rows["app_post_processing"] = {"error": str(e)}
+
     # ---------------- e2e: host (pinned) buffers through the C ABI
     e2e = None
     if not args.no_e2e:
@@ -279,8 +302,9 @@ def main():
             # algorithmic bytes of the dominant kernel per launch: every input sample once + what it writes
             out_bytes = {"multires_fft_8192": 6 * 4, "multires_fft_4096": 20 * 4, "multires_fft_2048": 102 * 4,
                          "multires_fft_1024": 384 * 4, "true_peak": 8, "kweight_lufs": 8, "meter_stats": 20,
-                         "blockdft_gemm": 128 * 4, "blockdft_asm_8192": 6 * 4}.get(dom, 0)
-            in_bytes = 16 if dom == "meter_stats" else (128 * 4 if dom.startswith("blockdft_asm") else HOP * 4)
+                         "blockdft_gemm": 128 * 4, "blockdft_tc_gemm": 512 * 4, "blockdft_asm_8192": 6 * 4,
+                         "blockdft_asm_4096": 20 * 4}.get(dom, 0)
+            in_bytes = {"meter_stats": 16, "blockdft_asm_8192": 100 * 4, "blockdft_asm_4096": 400 * 4}.get(dom, HOP * 4)
             alg = ch_hops * (in_bytes + out_bytes)
             ach = alg / (ktimes[dom] / 1e3) / 1e9
             traffic = None
@@ -311,7 +335,7 @@ def main():
             "roofline_fp32": {"flop_per_channel_hop": FLOP_PER_HOP, "achieved_tflops": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12,
                               "peak_tflops_nominal": FP32_PEAK_TFLOPS,
                               "frac": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12 / FP32_PEAK_TFLOPS},
-            "kernel_ms": ktimes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "kernel_ms": ktimes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "next_rows": next_rows,
             "final_rows_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
