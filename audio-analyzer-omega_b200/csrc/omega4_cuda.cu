@@ -301,6 +301,27 @@ struct DevBuf {
 
 struct KernelTime { char name[32]; cudaEvent_t e0, e1; };
 
+// side stream + fork/join events of one caller stream (plan-level for device calls, one per host slot)
+struct SideCtx {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_tp = nullptr, ev_join = nullptr;
+    int ensure() {
+        if (side) return OMEGA4_OK;
+        CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_tp, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        return OMEGA4_OK;
+    }
+    void release() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_tp) cudaEventDestroy(ev_tp);
+        if (ev_join) cudaEventDestroy(ev_join);
+        side = nullptr; ev_fork = ev_tp = ev_join = nullptr;
+    }
+};
+
 struct omega4_plan {
     int device = 0;
     int sample_rate = 48000, hop = 512, n_res = 0, T = 0, W = OMEGA4_METER_WINDOW;
@@ -326,14 +347,14 @@ struct omega4_plan {
     struct Slot {
         cudaStream_t s = nullptr;
         DevBuf in, in16, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
+        SideCtx sc;
     };
     static constexpr int N_SLOTS = 4;
     Slot slots[N_SLOTS];
     size_t host_chunk_bytes = (size_t)1536 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
     // OMEGA4_FLAG_CONCURRENT_METERS: the K-weighting + stats kernels run on a side stream, forked /
     // joined with events on the caller's stream
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_tp = nullptr, ev_join = nullptr;
+    SideCtx sc;
     long long launches = 0;
     std::vector<KernelTime> times;
     size_t n_times = 0;
@@ -645,15 +666,12 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
     for (auto& sl : p->slots) {
         sl.in.release(); sl.comb.release(); sl.met.release(); sl.lufs.release(); sl.tp.release(); sl.state.release();
-        sl.q.release(); sl.in16.release();
+        sl.q.release(); sl.in16.release(); sl.sc.release();
         for (auto& m : sl.mag) m.release();
         if (sl.s) cudaStreamDestroy(sl.s);
     }
     for (auto& t : p->times) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
-    if (p->side) cudaStreamDestroy(p->side);
-    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_tp) cudaEventDestroy(p->ev_tp);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    p->sc.release();
     cudaGetLastError();
     delete p;
 }
@@ -735,24 +753,26 @@ static int launch_blockdft_gemm(int bn, const BlockDftGemmArgs& a, cudaStream_t 
 
 static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long long ch_stride, int n_ch,
                           int n_hops, int hist, float* combined, float* const* mags, float* meters,
-                          double* lufs, double* tp, double* state, int flags, DevBuf* qbuf) {
+                          double* lufs, double* tp, double* state, int flags, DevBuf* qbuf, SideCtx* sc) {
     const bool timing = (flags & OMEGA4_FLAG_TIME_KERNELS) != 0;
     if (timing) p->n_times = 0;
     if (((uintptr_t)x & 15) != 0 || (ch_stride % 4) != 0)
         return fail(OMEGA4_ERR_INVALID, "samples must be 16-byte aligned with ch_stride a multiple of 4");
     const bool want_meters = meters || lufs || tp;
     const bool concurrent = want_meters && (flags & OMEGA4_FLAG_CONCURRENT_METERS);
-    cudaStream_t ms = s;                      // stream of the K-weighting + stats kernels
+    // default: the deque-statistics kernel (one warp per channel, latency bound, few resources) runs on a
+    // side stream underneath the FFT kernels that follow on the caller's stream
+    const bool stats_aside = !concurrent && meters && combined && !(flags & OMEGA4_FLAG_SERIAL_STATS);
+    cudaStream_t ms = s;                      // stream of the K-weighting kernel
+    cudaStream_t ss = s;                      // stream of the statistics kernel
+    if (concurrent || stats_aside) {
+        int rc = sc->ensure(); if (rc) return rc;
+        ss = sc->side;
+    }
     if (concurrent) {
-        if (!p->side) {
-            CK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&p->ev_tp, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-        }
-        ms = p->side;
-        CK(cudaEventRecord(p->ev_fork, s));
-        CK(cudaStreamWaitEvent(ms, p->ev_fork, 0));
+        ms = sc->side;
+        CK(cudaEventRecord(sc->ev_fork, s));
+        CK(cudaStreamWaitEvent(ms, sc->ev_fork, 0));
     }
     // ---- meters first: K-weighting on the meter stream, true peak on the caller's stream
     if (want_meters) {
@@ -788,9 +808,9 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             if (rc) return rc;
         }
         if (meters) {
-            if (concurrent) {
-                CK(cudaEventRecord(p->ev_tp, s));
-                CK(cudaStreamWaitEvent(ms, p->ev_tp, 0));
+            if (concurrent || stats_aside) {
+                CK(cudaEventRecord(sc->ev_tp, s));
+                CK(cudaStreamWaitEvent(ss, sc->ev_tp, 0));
             }
             StatsArgs st;
             memset(&st, 0, sizeof st);
@@ -803,11 +823,11 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 state = (double*)p->h_state.p;
             }
             st.state = state;
-            Bracket b(p, ms, timing, "meter_stats");
-            int rc = launch_stats(st, ms);
+            Bracket b(p, ss, timing, "meter_stats");
+            int rc = launch_stats(st, ss);
             if (rc) return rc;
         }
-        if (concurrent) CK(cudaEventRecord(p->ev_join, ms));
+        if (concurrent || stats_aside) CK(cudaEventRecord(sc->ev_join, ss));
     }
     // ---- multi-resolution FFTs (+ fused combine) on the caller's stream
     const bool fused = p->disjoint;
@@ -922,7 +942,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c);
         CK(cudaGetLastError());
     }
-    if (concurrent) CK(cudaStreamWaitEvent(s, p->ev_join, 0));
+    if (concurrent || stats_aside) CK(cudaStreamWaitEvent(s, sc->ev_join, 0));
     return OMEGA4_OK;
 }
 
@@ -951,10 +971,10 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
                                     d_in + (hist_al - hist_samples), dstride, s);
             if (rc) return rc;
             return analyze_device(p, s, d_in + hist_al, dstride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
-                                  lufs_inst, tp_db, meter_state, flags, &p->scratch_q);
+                                  lufs_inst, tp_db, meter_state, flags, &p->scratch_q, &p->sc);
         }
         return analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
-                              lufs_inst, tp_db, meter_state, flags, &p->scratch_q);
+                              lufs_inst, tp_db, meter_state, flags, &p->scratch_q, &p->sc);
     }
     if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
 
@@ -1030,7 +1050,7 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
             }
         const int fl = (flags & ~OMEGA4_FLAG_CONCURRENT_METERS) | ((meter_state == nullptr) ? OMEGA4_FLAG_FRESH_METERS : 0);
         rc = analyze_device(p, sl.s, d_in + hist_al, dstride, nc, n_hops, (int)hist, d_comb, any_mag ? d_mag : nullptr,
-                            d_met, d_lufs, d_tp, d_state, fl, &sl.q);
+                            d_met, d_lufs, d_tp, d_state, fl, &sl.q, &sl.sc);
         if (rc) return rc;
         const size_t r0 = (size_t)c0 * n_hops;
         if (combined) CK(cudaMemcpyAsync(combined + r0 * p->T, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, sl.s));

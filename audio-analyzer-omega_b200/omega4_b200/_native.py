@@ -28,6 +28,7 @@ FLAG_CONCURRENT_METERS = 4
 FLAG_NO_BLOCKDFT = 8
 FLAG_NO_TENSOR = 16
 FLAG_TENSOR = 32
+FLAG_SERIAL_STATS = 64
 ABI_VERSION = 1
 
 #: every symbol include/omega4_cuda.h declares (checked by tests/test_abi_symbols.py)

@@ -53,6 +53,9 @@ extern "C" {
                                                     of the tensor cores (tcgen05 kind::tf32, 3xTF32 split precision) */
 #define OMEGA4_FLAG_TENSOR 32                    /* force the tensor-core GEMM when the plan default is off (OMEGA4_TENSOR=0) */
 
+#define OMEGA4_FLAG_SERIAL_STATS 64               /* keep the deque-statistics kernel on the caller's stream (default: it
+                                                    runs on an internal side stream underneath the FFT kernels) */
+
 typedef struct omega4_plan omega4_plan;
 
 /* Everything that defines the reference's behaviour is DATA computed on the host with the
