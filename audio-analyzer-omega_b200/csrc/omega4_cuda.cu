@@ -1417,8 +1417,14 @@ extern "C" int omega4_bars_run(omega4_bars* b, void* stream, int mem, const floa
     }
     const size_t smem = bars_smem_bytes(b->T, b->n_valid);
     if (smem > 200 * 1024) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel");
-    CK(cudaFuncSetAttribute(bars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bars_kernel<<<n_ch, BARS_WARPS * 32, smem, s>>>(a);
+    if (b->T <= 512) CK(cudaFuncSetAttribute(bars_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(bars_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (b->T > 32 * BARS_MAXV) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel (max 1024 bins)");
+    a.seg = n_ch >= 1024 ? 4 * BARS_SEG : BARS_SEG;              // fewer warm-up replays when channels alone fill the GPU
+    const long long grid = (long long)n_ch * ((n_hops + a.seg - 1) / a.seg);
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "bars grid too large");
+    if (b->T <= 512) bars_kernel<16><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
+    else bars_kernel<32><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
     CK(cudaGetLastError());
     if (mem == OMEGA4_MEM_HOST) {
         CK(cudaMemcpyAsync(band_values, a.bars_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));

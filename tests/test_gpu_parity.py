@@ -308,6 +308,24 @@ def test_app_post_processing_golden_and_state():
     post.close()
 
 
+def test_app_post_processing_long_rows_use_segments():
+    """More than 512 hops per channel: the kernel cuts the rows into segments that rebuild the smoothing
+    state by replaying the 128 rows before them -- identical to the sequential recurrence to 1e-9."""
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    rng = np.random.default_rng(8)
+    spec = np.abs(rng.standard_normal((2, 1300, 512))).astype(np.float32) * np.linspace(2.0, 0.01, 512, dtype=np.float32)
+    spec[1, 600:640] = 0.0
+    post = SpectrumPostProcessor(512)
+    state = np.zeros((2, 1 + 437), np.float32)
+    got = post.process_host(spec, state=state)
+    for ch in range(2):
+        ref = O.OracleSpectrumPost(512)
+        want = np.stack([ref.process(row)[0] for row in spec[ch]])
+        assert np.abs(got[ch] - want).max() <= TOL_BAR
+        assert np.abs(state[ch, 1:] - want[-1]).max() <= TOL_BAR and state[ch, 0] == 1.0
+    post.close()
+
+
 def test_app_post_processing_resident_batch_against_oracle(plan):
     """Device-resident chain: analyze -> combined -> band_values, against the numpy oracle."""
     import torch
