@@ -8,30 +8,37 @@
 // remainder, itself rounded to TF32 by the hardware), and three products are accumulated in fp32:
 //   x_hi e_hi + x_hi e_lo + x_lo e_hi        (the dropped x_lo e_lo term is 2^-22 relative)
 // which restores ~fp32 accuracy at 3x the tensor work -- still several times cheaper than the CUDA-core
-// GEMM or the FFT for the resolutions that need <= 512 columns.
+// GEMM or the FFT for the resolutions that need <= 512 columns.  The tensor-core accumulator truncates
+// instead of rounding (measured: error grows linearly with the number of accumulation steps), so the
+// large x_hi e_hi products and the 2^-11 smaller cross products go to SEPARATE TMEM accumulators and
+// are added once, in registers, in the epilogue: the main accumulator then sees 64 steps, not 192.
 //
-// One CTA = 256 hop blocks (two M = 128 accumulators) x 256 columns (one N = 256 half), K in chunks of
-// 16 samples.  Shared-memory operand tiles use the canonical K-major SWIZZLE_64B layout
+// One CTA = 128 hop blocks x 256 columns (TC_MH = 1; or 256 x 128 with TC_MH = 2); TMEM: [main | cross]
+// x 256 columns = all 512.  K in chunks of 16 samples.  Shared-memory operand tiles use the canonical K-major SWIZZLE_64B layout
 // (8-row groups of 64-byte rows, 16-byte chunk index XOR (row >> 1) & 3, SBO = 512 B):
 //   A_hi / A_lo: written by all 256 threads (LDG.128 of the raw samples, split, STS.128)
 //   B_hi / B_lo: the constant E table, pre-swizzled on the host into per-chunk byte images and
 //                fetched with one-dimensional cp.async.bulk (TMA without a tensor map) + mbarrier tx
-// Thread 0 issues the MMAs (12 per chunk) and commits them to the stage's mbarrier; the other
-// threads run ahead producing the next A chunk.  Epilogue: tcgen05.ld 32x32b -> registers -> Q.
+// A ninth warp's lane 0 requests the B images and issues the MMAs (12 per chunk), committing them to
+// the stage's mbarrier; the 256 producer threads run ahead by up to STAGES chunks (no block-wide
+// barrier in the main loop).  Epilogue: tcgen05.ld 32x32b -> registers (main + cross) -> Q.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace o4 {
 
-constexpr int TC_BM = 256;          // hop blocks per CTA (2 x UMMA M = 128)
-constexpr int TC_BN = 256;          // columns per CTA (UMMA N)
+#ifndef TC_MH
+#define TC_MH 1                     // row halves of 128 hop blocks per CTA (1 or 2); TC_MH * TC_BN = 256
+#endif
+constexpr int TC_BM = 128 * TC_MH;  // hop blocks per CTA
+constexpr int TC_BN = 256 / TC_MH;  // columns per CTA (UMMA N)
 constexpr int TC_KC = 16;           // samples per K chunk: 64-byte rows
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 256;
-constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;     // 16 KB per (hi | lo)
-constexpr int TC_B_BYTES = TC_BN * TC_KC * 4;     // 16 KB per (hi | lo)
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
+constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;     // 8 / 16 KB per (hi | lo)
+constexpr int TC_B_BYTES = TC_BN * TC_KC * 4;     // 16 / 8 KB per (hi | lo)
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
 
 struct BlockDftTcArgs {
     const float* x;            // samples; block j of channel c = x + c*ch_stride + j*hop
@@ -39,10 +46,10 @@ struct BlockDftTcArgs {
     int hop;                   // K, multiple of TC_KC
     int n_ch;
     int j0, nb;
-    int n_halves;              // 1 or 2 column halves of 256
+    int n_halves;              // column tiles of TC_BN (1 .. 4)
     const uint8_t* Eimg;       // [n_halves][hop/KC][2 (hi, lo)][TC_B_BYTES] pre-swizzled operand images
     float* Q;                  // [n_ch][nb][qs]
-    int qs;                    // 256 * n_halves
+    int qs;                    // TC_BN * n_halves
 };
 
 // byte offset of (row, 16-byte chunk c in 0..3) inside a K-major SWIZZLE_64B tile of 64-byte rows
@@ -85,7 +92,7 @@ __device__ __forceinline__ uint64_t tc_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor: D = F32, A = B = TF32, K-major both, N = 256, M = 128
+// instruction descriptor: D = F32, A = B = TF32, K-major both, N = TC_BN, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
@@ -99,14 +106,35 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps 0..7 (256 threads) produce the A tiles and later run the epilogue; warp 8, lane 0
+// requests the B images (bulk TMA) and issues every tcgen05.mma.  Three mbarrier rings tie them together:
+//   bar_a[s]  256 arrivals  A_hi / A_lo of the stage are written and fenced for the async proxy
+//   bar_b[s]  tx bytes      the B image of the stage has landed
+//   bar_m[s]  tcgen05.commit: every MMA issued so far (in particular those reading stage s) has retired
+__global__ void __launch_bounds__(TC_THREADS + 32, 1)
 blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     extern __shared__ __align__(16) uint8_t tc_smem_raw[];
     // swizzled operand tiles need a 1024-byte aligned base (the swizzle is a function of address bits)
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    // [STAGES][A_hi | A_lo | B_hi | B_lo], then barriers and the TMEM base address
-    uint64_t* bar_b = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);     // B landed      [STAGES]
-    uint64_t* bar_m = bar_b + TC_STAGES;                                                   // MMAs retired  [STAGES]
+    uint64_t* bar_a = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* bar_b = bar_a + TC_STAGES;
+    uint64_t* bar_m = bar_b + TC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_m + TC_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,7 +148,9 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     const uint8_t* eimg = a.Eimg + (size_t)half * n_kc * 2 * TC_B_BYTES;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(bar_b + s, 1); tc_mbar_init(bar_m + s, 1); }
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc_mbar_init(bar_a + s, TC_THREADS); tc_mbar_init(bar_b + s, 1); tc_mbar_init(bar_m + s, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -133,112 +163,117 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    // A pieces of this thread: 1024 16-byte pieces per chunk, piece p = tid + 256 q -> row p/4, chunk p%4
-    const float4* a_src[4];
-    int a_off[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int p = tid + TC_THREADS * q;
-        const int row = p >> 2, c = p & 3;
-        int r = row0 + row;
-        if (r >= a.nb) r = a.nb - 1;                      // rows past the end: computed, never stored
-        a_src[q] = reinterpret_cast<const float4*>(xa + (long long)r * a.hop) + c;
-        a_off[q] = tc_sw64_offset(row, c);
-    }
-    float4 nxt[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) nxt[q] = __ldg(a_src[q]);
-
-    // B operand of chunk 0; afterwards iteration kc requests chunk kc + 1, one full iteration ahead
-    if (tid == 0) {
-        tc_mbar_expect_tx(bar_b, 2 * TC_B_BYTES);
-        tc_bulk_g2s(tiles + 2 * TC_A_BYTES, eimg, 2 * TC_B_BYTES, bar_b);
-    }
-    for (int kc = 0; kc < n_kc; ++kc) {
-        const int s = kc % TC_STAGES;
-        const uint32_t use = (uint32_t)(kc / TC_STAGES);
-        uint8_t* st = tiles + s * TC_STAGE_BYTES;
-        // stage (kc+1) % STAGES was last read by the MMAs of chunk kc - 2: once those have retired
-        // (a commit covers every earlier MMA, so chunk kc - 3's stage -- ours -- is free as well) the next
-        // B chunk can be requested and this chunk's A tiles written
-        if (kc >= 2) tc_mbar_wait(bar_m + (kc - 2) % TC_STAGES, (uint32_t)((kc - 2) / TC_STAGES) & 1);
-        if (tid == 0 && kc + 1 < n_kc) {
-            const int s1 = (kc + 1) % TC_STAGES;
-            tc_mbar_expect_tx(bar_b + s1, 2 * TC_B_BYTES);
-            tc_bulk_g2s(tiles + s1 * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)(kc + 1) * 2 * TC_B_BYTES,
-                        2 * TC_B_BYTES, bar_b + s1);
-        }
-        float4 cur[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
-        if (kc + 1 < n_kc) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) nxt[q] = __ldg(a_src[q] + (kc + 1) * (TC_KC / 4));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(cur[q].x) & 0xFFFFE000u); lo.x = cur[q].x - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(cur[q].y) & 0xFFFFE000u); lo.y = cur[q].y - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(cur[q].z) & 0xFFFFE000u); lo.z = cur[q].z - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(cur[q].w) & 0xFFFFE000u); lo.w = cur[q].w - hi.w;
-            *reinterpret_cast<float4*>(st + a_off[q]) = hi;
-            *reinterpret_cast<float4*>(st + TC_A_BYTES + a_off[q]) = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
-        __syncthreads();
-        if (tid == 0) {
-            tc_mbar_wait(bar_b + s, use & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = tc_smem_u32(st);
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh) {
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t d_ahi = tc_desc_sw64(sa + mh * (TC_A_BYTES / 2) + ks * 32);
-                    const uint64_t d_alo = tc_desc_sw64(sa + TC_A_BYTES + mh * (TC_A_BYTES / 2) + ks * 32);
-                    const uint64_t d_bhi = tc_desc_sw64(sa + 2 * TC_A_BYTES + ks * 32);
-                    const uint64_t d_blo = tc_desc_sw64(sa + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32);
-                    const uint32_t td = tmem + mh * TC_BN;
-                    tc_mma_tf32(td, d_ahi, d_bhi, (kc | ks) != 0);
-                    tc_mma_tf32(td, d_ahi, d_blo, 1);
-                    tc_mma_tf32(td, d_alo, d_bhi, 1);
-                }
+    if (warp == TC_THREADS / 32) {
+        // ===== MMA + B-operand issuer (one thread) =====
+        if (lane == 0) {
+            constexpr int AHEAD = TC_STAGES - 2;                          // B chunks requested ahead of use
+            for (int kc = 0; kc < AHEAD && kc < n_kc; ++kc) {
+                tc_mbar_expect_tx(bar_b + kc, 2 * TC_B_BYTES);
+                tc_bulk_g2s(tiles + kc * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kc * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + kc);
             }
-            tc_commit(bar_m + s);
+            for (int kc = 0; kc < n_kc; ++kc) {
+                const int s = kc % TC_STAGES;
+                const uint32_t use = (uint32_t)(kc / TC_STAGES);
+                // request B of chunk kc + AHEAD: its stage was last read by chunk kc + AHEAD - STAGES = kc - 2
+                const int kb = kc + AHEAD;
+                if (kb < n_kc) {
+                    if (kc >= 2) tc_mbar_wait(bar_m + (kc - 2) % TC_STAGES, (uint32_t)((kc - 2) / TC_STAGES) & 1);
+                    const int sb = kb % TC_STAGES;
+                    tc_mbar_expect_tx(bar_b + sb, 2 * TC_B_BYTES);
+                    tc_bulk_g2s(tiles + sb * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kb * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + sb);
+                }
+                tc_mbar_wait(bar_a + s, use & 1);
+                tc_mbar_wait(bar_b + s, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = tc_smem_u32(tiles + s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int mh = 0; mh < TC_MH; ++mh) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t d_ahi = tc_desc_sw64(sa + mh * (TC_A_BYTES / TC_MH) + ks * 32);
+                        const uint64_t d_alo = tc_desc_sw64(sa + TC_A_BYTES + mh * (TC_A_BYTES / TC_MH) + ks * 32);
+                        const uint64_t d_bhi = tc_desc_sw64(sa + 2 * TC_A_BYTES + ks * 32);
+                        const uint64_t d_blo = tc_desc_sw64(sa + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32);
+                        const uint32_t t_main = tmem + mh * TC_BN, t_cross = tmem + 256 + mh * TC_BN;
+                        tc_mma_tf32(t_main, d_ahi, d_bhi, (kc | ks) != 0);
+                        tc_mma_tf32(t_cross, d_ahi, d_blo, (kc | ks) != 0);
+                        tc_mma_tf32(t_cross, d_alo, d_bhi, 1);
+                    }
+                }
+                tc_commit(bar_m + s);
+            }
         }
-    }
-    // all MMAs retired <=> the last commit has arrived (a commit tracks every prior tcgen05.mma)
-    {
-        const int last = n_kc - 1;
-        tc_mbar_wait(bar_m + (last % TC_STAGES), (uint32_t)(last / TC_STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    // epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 of accumulator w / 4
-    {
-        const int mh = warp >> 2, quad = warp & 3;
+    } else {
+        // ===== A producers: 4 TC_BM 16-byte pieces per chunk, piece p = tid + 256 q -> row p/4, chunk p%4 =====
+        constexpr int NQ = TC_BM * 4 / TC_THREADS;
+        const float4* a_src[NQ];
+        int a_off[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int p = tid + TC_THREADS * q;
+            const int row = p >> 2, c = p & 3;
+            int r = row0 + row;
+            if (r >= a.nb) r = a.nb - 1;                      // rows past the end: computed, never stored
+            a_src[q] = reinterpret_cast<const float4*>(xa + (long long)r * a.hop) + c;
+            a_off[q] = tc_sw64_offset(row, c);
+        }
+        float4 nxt[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) nxt[q] = __ldg(a_src[q]);
+        for (int kc = 0; kc < n_kc; ++kc) {
+            const int s = kc % TC_STAGES;
+            uint8_t* st = tiles + s * TC_STAGE_BYTES;
+            float4 cur[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) cur[q] = nxt[q];
+            if (kc + 1 < n_kc) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) nxt[q] = __ldg(a_src[q] + (kc + 1) * (TC_KC / 4));
+            }
+            // the MMAs that read this stage (chunk kc - STAGES) must have retired before it is overwritten
+            if (kc >= TC_STAGES) tc_mbar_wait(bar_m + s, (uint32_t)(kc / TC_STAGES - 1) & 1);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(cur[q].x) & 0xFFFFE000u); lo.x = cur[q].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(cur[q].y) & 0xFFFFE000u); lo.y = cur[q].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(cur[q].z) & 0xFFFFE000u); lo.z = cur[q].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(cur[q].w) & 0xFFFFE000u); lo.w = cur[q].w - hi.w;
+                *reinterpret_cast<float4*>(st + a_off[q]) = hi;
+                *reinterpret_cast<float4*>(st + TC_A_BYTES + a_off[q]) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
+            tc_mbar_arrive(bar_a + s);
+        }
+        // all MMAs retired <=> the last commit has arrived (a commit tracks every prior tcgen05.mma)
+        {
+            const int last = n_kc - 1;
+            tc_mbar_wait(bar_m + (last % TC_STAGES), (uint32_t)(last / TC_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31; the two warp groups split the row halves
+        // (TC_MH = 2) or the columns (TC_MH = 1); main + cross accumulators are added in registers
+        const int grp = warp >> 2, quad = warp & 3;
+        const int mh = (TC_MH == 2) ? grp : 0;
+        const int c0 = (TC_MH == 2) ? 0 : grp * (TC_BN / 2);
+        constexpr int NCG = (TC_MH == 2) ? TC_BN / 32 : TC_BN / 64;
         const int row = row0 + mh * 128 + quad * 32 + lane;
-        float* qrow = a.Q + ((size_t)ch * a.nb + (row < a.nb ? row : 0)) * a.qs + half * TC_BN;
+        float* qrow = a.Q + ((size_t)ch * a.nb + (row < a.nb ? row : 0)) * a.qs + half * TC_BN + c0;
 #pragma unroll 1
-        for (int cg = 0; cg < TC_BN / 32; ++cg) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mh * TC_BN + cg * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr) : "memory");
+        for (int cg = 0; cg < NCG; ++cg) {
+            uint32_t v[32], c[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mh * TC_BN + c0 + cg * 32);
+            tc_tmem_ld32(taddr, v);
+            tc_tmem_ld32(taddr + 256, c);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < a.nb) {
                 float4* dst = reinterpret_cast<float4*>(qrow + cg * 32);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(c[4 * i]),
+                                         __uint_as_float(v[4 * i + 1]) + __uint_as_float(c[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]) + __uint_as_float(c[4 * i + 2]),
+                                         __uint_as_float(v[4 * i + 3]) + __uint_as_float(c[4 * i + 3]));
             }
         }
     }
@@ -248,6 +283,6 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-inline size_t blockdft_tc_smem_bytes() { return (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * TC_STAGES * 8 + 16 + 1024; }
+inline size_t blockdft_tc_smem_bytes() { return (size_t)TC_STAGES * TC_STAGE_BYTES + 3 * TC_STAGES * 8 + 16 + 1024; }
 
 }  // namespace o4

@@ -412,7 +412,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
                             const std::vector<std::vector<int>>& lo, bool tensor, SparseSet* set) {
     const int H = d->hop;
     if ((H % (tensor ? TC_KC : BD_KC)) != 0) return OMEGA4_OK;
-    const int max_cols = tensor ? 2 * TC_BN : 128;
+    const int max_cols = tensor ? 512 : 128;              // all TMEM columns / the widest CUDA-core tile
     int order[OMEGA4_MAX_RES];
     for (int r = 0; r < d->n_res; ++r) order[r] = r;
     for (int i = 0; i < d->n_res; ++i)                 // largest transform first
@@ -519,7 +519,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
     }
     // tensor-core operand: per column half and K chunk, the (hi, lo) TF32 split of E^T as byte images of
     // the K-major SWIZZLE_64B shared-memory layout
-    set->n_halves = cols <= TC_BN ? 1 : 2;
+    set->n_halves = (cols + TC_BN - 1) / TC_BN;
     set->qs = set->n_halves * TC_BN;
     const int nkc = H / TC_KC;
     std::vector<uint8_t> img((size_t)set->n_halves * nkc * 2 * TC_B_BYTES, 0);
@@ -893,7 +893,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 const long long grid = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
                 if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
                 Bracket b(p, s, timing, "blockdft_tc_gemm");
-                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, s>>>(g);
+                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS + 32, smem, s>>>(g);
                 CK(cudaGetLastError());
             } else {
                 BlockDftGemmArgs g;

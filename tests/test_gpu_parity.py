@@ -384,6 +384,65 @@ def test_s16_decode_matches_capture_formula():
     assert np.array_equal(want, pcm.astype(np.float32) * np.float32(1.0 / 32768.0))
 
 
+def test_blockdft_edge_shapes_match_full_fft(plan):
+    """Short inputs (fewer hops than the longest window has blocks), odd channel counts, padded row
+    strides and carried history: the hop-block paths must agree with the full-FFT evaluation."""
+    import torch
+    from omega4_b200 import _native as N
+    from omega4_b200.batch.synth import synth_streams
+    for n_ch, n_hops in ((1, 1), (3, 3), (5, 15), (5, 16), (2, 17), (7, 300)):
+        x = synth_streams(n_ch, 1, n_hops * HOP).reshape(n_ch, -1)
+        ref = plan.analyze_host(x, want_meters=False, flags=N.FLAG_NO_BLOCKDFT)["combined"]
+        scale = ref.max(axis=-1, keepdims=True) + 1e-20
+        for fl in (0, N.FLAG_NO_TENSOR):
+            got = plan.analyze_host(x, want_meters=False, flags=fl)["combined"]
+            assert np.array_equal(got == 0, ref == 0), (n_ch, n_hops, fl)
+            assert (np.abs(got - ref) / scale).max() < 2e-5, (n_ch, n_hops, fl)
+    # padded row stride + history carried in front of the rows (device pointers)
+    n_hops, hist = 40, 7680
+    x = synth_streams(3, 1, hist + n_hops * HOP).reshape(3, -1)
+    buf = torch.zeros((3, hist + n_hops * HOP + 64), device="cuda")
+    buf[:, :x.shape[1]] = torch.from_numpy(x).cuda()
+    outs = []
+    for fl in (0, N.FLAG_NO_TENSOR, N.FLAG_NO_BLOCKDFT):
+        comb = torch.empty((3, n_hops, 512), device="cuda")
+        plan.analyze_device(buf, n_hops, hist_samples=hist, combined=comb, flags=fl)
+        torch.cuda.synchronize()
+        outs.append(comb.cpu().numpy())
+    whole = plan.analyze_host(x, want_meters=False, flags=N.FLAG_NO_BLOCKDFT)["combined"][:, hist // HOP:]
+    assert np.array_equal(outs[2], whole)                               # same frames, same FFT path: identical
+    scale = whole.max(axis=-1, keepdims=True) + 1e-20
+    assert (np.abs(outs[0] - whole) / scale).max() < 2e-5 and (np.abs(outs[1] - whole) / scale).max() < 2e-6
+    assert np.all(outs[0][:, 0, 1:6] > 0)                                # the 8192 window is already full at hop 0
+
+
+def test_new_entry_points_reject_bad_arguments(plan):
+    import ctypes as C
+    from omega4_b200 import _native as N, Omega4CudaError
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    lib = N.lib()
+    w = N.Weighting()
+    w.n_sections = 5
+    assert lib.omega4_plan_set_weighting(plan.handle, C.byref(w)) == -1
+    w.n_sections = 1; w.order[0] = 3
+    assert lib.omega4_plan_set_weighting(plan.handle, C.byref(w)) == -3
+    w.order[0] = 2; w.blend = 1
+    for j, v in enumerate((1.0, -1.9, 0.95)):
+        w.a[0][j] = v; w.b[0][j] = v
+    assert lib.omega4_plan_set_weighting(plan.handle, C.byref(w)) == -1          # blend needs two sections
+    assert lib.omega4_plan_set_weighting(plan.handle, None) == 0                 # NULL restores K
+    assert plan.analyze_s16_host(np.zeros((0, 512, 2), np.int16))["n_hops"] == 1
+    assert plan.analyze_s16_host(np.zeros((2, 100), np.int16)).get("combined") is None   # less than one hop
+    assert lib.omega4_analyze_s16(plan.handle, None, N.MEM_HOST, None, 0, 1, 2, 1, 0, None, None, None, None, None, None, 0) == -1
+    post = SpectrumPostProcessor(512)
+    with pytest.raises(Omega4CudaError):
+        post.process(np.zeros(100, np.float32))
+    d = N.BarsDesc()
+    d.spectrum_len, d.n_bars = 512, 0
+    assert not lib.omega4_bars_create(C.byref(d), 0) and b"bad bars descriptor" in lib.omega4_last_error()
+    post.close()
+
+
 # ------------------------------------------------------------------ meters
 def test_meters_stream_golden(plan, golden):
     g = golden("meters_stream.npz")

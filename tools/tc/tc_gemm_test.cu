@@ -10,7 +10,7 @@ using namespace o4;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
 int main() {
-    const int hop = 512, nb = 1000, n_ch = 3, halves = 2, cols = 512;
+    const int hop = 512, nb = 1000, n_ch = 3, cols = 512, halves = cols / TC_BN;
     const int j0 = 0;
     std::vector<float> x((size_t)n_ch * nb * hop), E((size_t)hop * cols);
     srand(1);
@@ -39,10 +39,10 @@ int main() {
     CK(cudaFuncSetAttribute(blockdft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = ((nb + TC_BM - 1) / TC_BM) * n_ch * halves;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    blockdft_tc_kernel<<<grid, TC_THREADS, smem>>>(a);
+    blockdft_tc_kernel<<<grid, TC_THREADS + 32, smem>>>(a);
     CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    for (int i = 0; i < 10; ++i) blockdft_tc_kernel<<<grid, TC_THREADS, smem>>>(a);
+    for (int i = 0; i < 10; ++i) blockdft_tc_kernel<<<grid, TC_THREADS + 32, smem>>>(a);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     std::vector<float> q((size_t)n_ch * nb * cols);
