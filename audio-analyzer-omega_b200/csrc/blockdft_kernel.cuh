@@ -191,14 +191,19 @@ struct BlockDftAsmArgs {
     int fa;                    // frames per CTA
 };
 
+// Register blocking: one work item = (needed bin ki, group of 4 consecutive frames).  The four frames
+// share all but one Q row per block step, so a sliding window of four rows lives in registers and
+// every step loads NT window terms + NT new Q values for 4 NT complex MACs (0.5 LDS per MAC instead
+// of 2).  Lanes run over ki (Q stride NT float2: conflict free; T is stored [b][t][ki]).
+template <int NT>
 __global__ void __launch_bounds__(256)
 blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nc = a.nk * a.nt;                           // complex columns of this resolution
-    const int rs = nc | 1;                                // odd float2 row stride: conflict-free across frames
-    float2* Qs = reinterpret_cast<float2*>(smem_raw);     // [fa + B - 1][rs]
-    float2* Ts = Qs + (size_t)(a.fa + a.B - 1) * rs;      // [nk][B][nt]
-    float* mags = reinterpret_cast<float*>(Ts + (size_t)a.nk * a.B * a.nt);   // [fa][nk]
+    const int nc = a.nk * NT;                             // complex columns of this resolution
+    const int rs = nc | 1;                                // odd float2 row stride
+    float2* Qs = reinterpret_cast<float2*>(smem_raw);     // [fa + B - 1 + 3][rs]
+    float2* Ts = Qs + (size_t)(a.fa + a.B + 2) * rs;      // [B][NT][nk]
+    float* mags = reinterpret_cast<float*>(Ts + (size_t)a.nk * a.B * NT);   // [fa][nk]
 
     const int tiles_per_ch = (a.n_frames + a.fa - 1) / a.fa;
     const int ch = blockIdx.x / tiles_per_ch;
@@ -206,11 +211,14 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
     const int nf = min(a.fa, a.n_frames - f0);
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < a.nk * a.B * a.nt; i += 256) Ts[i] = a.T[i];
-    // Q rows of blocks f0 + 1 - B .. f0 + nf - 1  (row index in Q = block - j0); rows before j0
-    // belong to frames that are not filled yet and are never read
+    for (int i = tid; i < a.nk * a.B * NT; i += 256) {    // global [ki][b][t] -> shared [b][t][ki]
+        const int ki = i / (a.B * NT), r = i % (a.B * NT);
+        Ts[r * a.nk + ki] = a.T[i];
+    }
+    // Q rows of blocks f0 + 1 - B .. (row index in Q = block - j0); rows before j0 belong to frames that
+    // are not filled yet, rows past the channel's last block to the unused tail of the last frame group
     const int jb = f0 + 1 - a.B;
-    const int nrows = nf + a.B - 1;
+    const int nrows = a.fa + a.B + 2;
     const float* qch = a.Q + (size_t)ch * a.nb * a.qs + a.col0;
     for (int i = tid; i < nrows * nc; i += 256) {
         const int r = i / nc, c = i % nc;
@@ -220,20 +228,38 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
         Qs[r * rs + c] = v;
     }
     __syncthreads();
-    for (int it = tid; it < a.fa * a.nk; it += 256) {
-        const int fl = it % a.fa, ki = it / a.fa;
-        if (fl >= nf) continue;
-        float2 acc = make_float2(0.f, 0.f);
-        const float2* tq = Ts + (size_t)ki * a.B * a.nt;
+    const int ng = (nf + 3) >> 2;
+    for (int it = tid; it < ng * a.nk; it += 256) {
+        const int ki = it % a.nk, fl = (it / a.nk) << 2;
+        float2 acc[4], w[4][NT];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+        const float2* qcol = Qs + fl * rs + ki * NT;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) w[j + 1][t] = qcol[j * rs + t];
         for (int b = 0; b < a.B; ++b) {
-            const float2* qrow = Qs + (fl + b) * rs + ki * a.nt;
-            for (int t = 0; t < a.nt; ++t) {
-                const float2 q = qrow[t], w = tq[b * a.nt + t];
-                acc.x = fmaf(q.x, w.x, fmaf(-q.y, w.y, acc.x));
-                acc.y = fmaf(q.x, w.y, fmaf(q.y, w.x, acc.y));
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) w[j][t] = w[j + 1][t];
+                w[3][t] = qcol[(b + 3) * rs + t];
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float2 tw = Ts[(b * NT + t) * a.nk + ki];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[j].x = fmaf(w[j][t].x, tw.x, fmaf(-w[j][t].y, tw.y, acc[j].x));
+                    acc[j].y = fmaf(w[j][t].x, tw.y, fmaf(w[j][t].y, tw.x, acc[j].y));
+                }
             }
         }
-        mags[fl * a.nk + ki] = sqrtf(fmaf(acc.x, acc.x, acc.y * acc.y)) * a.kw[ki];
+        const float kw = a.kw[ki];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (fl + j < nf) mags[(fl + j) * a.nk + ki] = sqrtf(fmaf(acc[j].x, acc[j].x, acc[j].y * acc[j].y)) * kw;
     }
     __syncthreads();
     for (int it = tid; it < nf * a.n_tb; it += 256) {
@@ -252,7 +278,7 @@ blockdft_assemble_kernel(const __grid_constant__ BlockDftAsmArgs a) {
 
 inline size_t blockdft_assemble_smem_bytes(int nk, int nt, int B, int fa) {
     const int nc = nk * nt, rs = nc | 1;
-    return (size_t)(fa + B - 1) * rs * sizeof(float2) + (size_t)nk * B * nt * sizeof(float2) +
+    return (size_t)(fa + B + 2) * rs * sizeof(float2) + (size_t)nk * B * nt * sizeof(float2) +
            (size_t)fa * nk * sizeof(float) + 16;
 }
 

@@ -918,13 +918,14 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             a.tb_frac = ri.tb_frac; a.wnum = ri.weight; a.wden = ri.weight;
             a.fa = blockdft_assemble_frames(sp.nk, sp.nt, sp.B);
             const size_t smem = blockdft_assemble_smem_bytes(sp.nk, sp.nt, sp.B, a.fa);
-            CK(cudaFuncSetAttribute(blockdft_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            auto kern = sp.nt == 5 ? blockdft_assemble_kernel<5> : (sp.nt == 3 ? blockdft_assemble_kernel<3> : blockdft_assemble_kernel<1>);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const long long grid = (long long)((n_hops + a.fa - 1) / a.fa) * n_ch;
             if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft assemble grid too large");
             char name[32];
             snprintf(name, sizeof name, "blockdft_asm_%d", ri.n);
             Bracket b(p, s, timing, name);
-            blockdft_assemble_kernel<<<(unsigned)grid, 256, smem, s>>>(a);
+            kern<<<(unsigned)grid, 256, smem, s>>>(a);
             CK(cudaGetLastError());
         }
     }
