@@ -131,13 +131,25 @@ static int default_rounds(int n_frames, int conc) {
     return r;
 }
 
+static void fill_truepeak_steps(TruePeakArgs* t) {
+    const double two_pi = 6.283185307179586476925287;
+    for (int p = 1; p <= 3; ++p) {
+        for (int j = 0; j < 16; ++j) {
+            const int jj = j < 8 ? j : j - 16;
+            t->step[p - 1][j] = make_float2((float)cos(two_pi * p * jj / 64.0), (float)sin(two_pi * p * jj / 64.0));
+        }
+        t->nyq[p - 1] = (float)cos(two_pi * p / 8.0);
+    }
+}
+
 static int launch_truepeak(const TruePeakArgs& a, cudaStream_t s) {
-    constexpr int L = 10;     // W = 2048 -> 1024 complex points
+    constexpr int L = 11;     // W = 2048 complex points: two real frames per transform
     using S = FftShape<L>;
     const size_t smem = truepeak_smem_bytes<L>();
     CK(cudaFuncSetAttribute(truepeak_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int fpc = a.rounds * S::CONC;
-    const long long grid = (long long)((a.n_frames + fpc - 1) / fpc) * a.n_ch;
+    const int ppc = a.rounds * S::CONC;                    // frame pairs per CTA
+    const int n_pairs = (a.n_frames + 1) / 2;
+    const long long grid = (long long)((n_pairs + ppc - 1) / ppc) * a.n_ch;
     if (grid <= 0) return OMEGA4_OK;
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "truepeak grid too large");
     truepeak_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
@@ -336,7 +348,8 @@ struct omega4_plan {
     KwBiquad kw[4];               // active weighting program (omega4_plan_set_weighting)
     int kw_nsec = 2, kw_blend = 1, kw_gate = 1;
     double kw_gain = 1.0;
-    Twiddles tw_meter;
+    Twiddles tw_meter;            // W-point complex transform of the true-peak kernel
+    float2* tp_rot = nullptr;     // [3][W] fractional-delay factors
     SparseSet set_cc;             // fp32 CUDA-core GEMM: up to 128 columns
     SparseSet set_tc;             // 3xTF32 tcgen05 GEMM: up to 512 columns
     bool tensor_default = true;   // OMEGA4_TENSOR=0 makes the CUDA-core GEMM the default
@@ -625,7 +638,24 @@ static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
     build_biquad(d->kw_coeffs + 0, d->kw_coeffs + 3, 2, &p->kw_default[0]);
     build_biquad(d->kw_coeffs + 6, d->kw_coeffs + 9, 2, &p->kw_default[1]);
     set_weighting_k(p);
-    rc = get_twiddles(p->device, ilog2(p->W) - 1, &p->tw_meter); if (rc) return rc;
+    rc = get_twiddles(p->device, ilog2(p->W), &p->tw_meter); if (rc) return rc;
+    {
+        const int W = p->W;
+        std::vector<float2> rot((size_t)3 * W);
+        const double two_pi = 6.283185307179586476925287;
+        for (int ph = 1; ph <= 3; ++ph)
+            for (int k = 0; k < W; ++k) {
+                float2 v;
+                if (k == W / 2) v = make_float2((float)cos(two_pi * ph / 8.0), 0.f);
+                else {
+                    const double f = (k < W / 2) ? (double)k : (double)k - W;
+                    const double ang = two_pi * f * ph / (4.0 * W);
+                    v = make_float2((float)cos(ang), (float)sin(ang));
+                }
+                rot[(size_t)(ph - 1) * W + k] = v;
+            }
+        rc = upload((void**)&p->tp_rot, rot.data(), rot.size() * sizeof(float2)); if (rc) return rc;
+    }
     return OMEGA4_OK;
 }
 
@@ -659,7 +689,7 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
         p->scratch_mag[r].release(); p->h_mag[r].release();
     }
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
-    cudaFree(p->hann64); cudaFree(p->hann32);
+    cudaFree(p->hann64); cudaFree(p->hann32); cudaFree(p->tp_rot);
     p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
     p->set_cc.release(); p->set_tc.release();
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
@@ -800,8 +830,9 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             t.x = x; t.x_is_f64 = 0; t.ch_stride = ch_stride; t.frame_stride = p->hop;
             t.frame_off0 = (long long)p->hop - p->W;
             t.n_ch = n_ch; t.n_frames = n_hops; t.first_frame = first_m;
-            t.rounds = default_rounds(n_hops, 4);
-            t.window = p->hann32; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
+            t.rounds = default_rounds((n_hops + 1) / 2, 2);
+            t.window = p->hann32; t.twM = p->tw_meter.twM; t.rot = p->tp_rot;
+            fill_truepeak_steps(&t);
             t.tp_out = tp;
             Bracket b(p, s, timing, "true_peak");
             int rc = launch_truepeak(t, s);
@@ -1169,8 +1200,9 @@ extern "C" int omega4_meter_frames(omega4_plan* p, void* stream, int mem, const 
         TruePeakArgs t;
         memset(&t, 0, sizeof t);
         t.x = d_fr; t.x_is_f64 = 1; t.ch_stride = 0; t.frame_stride = W; t.frame_off0 = 0;
-        t.n_ch = 1; t.n_frames = n_frames; t.first_frame = 0; t.rounds = default_rounds(n_frames, 4);
-        t.window = nullptr; t.twM = p->tw_meter.twM; t.twN = p->tw_meter.twN; t.tw4W = p->tw_meter.tw4W;
+        t.n_ch = 1; t.n_frames = n_frames; t.first_frame = 0; t.rounds = default_rounds((n_frames + 1) / 2, 2);
+        t.window = nullptr; t.twM = p->tw_meter.twM; t.rot = p->tp_rot;
+        fill_truepeak_steps(&t);
         t.tp_out = d_t;
         p->launches++;
         rc = launch_truepeak(t, s);

@@ -5,10 +5,18 @@
 // scipy's FFT-method resample of a real, even-length frame is: X = rfft(x); X[W/2] *= 0.5;
 // irfft(zero-padded X, 4W) * 4.  The pruned form used here (max error
 // 1.1e-15 against scipy in float64):  out[4n] = x[n], and for phase p in {1,2,3}
-//     out[4n+p] = irfft_W(Xp)[n],  Xp[k] = X[k] e^{+2 pi i k p/(4W)} (k < W/2),  Xp[W/2] = X[W/2] cos(pi p/4)
-// i.e. one forward and three inverse W-point real transforms, each done as a W/2-point complex
-// Stockham transform (fft_core.cuh).  Only max|.| of the inverse outputs is needed, so the last
-// stage of every inverse transform stays in registers.
+//     out[4n+p] = ifft_W(S_p)[n],   S_p[k] = X[k] e^{+2 pi i f(k) p/(4W)},  f(k) = k (k < W/2), k - W (k > W/2),
+//     S_p[W/2] = X[W/2] cos(pi p/4)
+// i.e. a quarter-, half- and three-quarter-sample delay applied in the frequency domain.
+//
+// TWO FRAMES PER TRANSFORM: consecutive frames a, b of a channel are packed as z = a + i b.  The delay
+// factors depend on the signed frequency only, so S_p = Z .* R_p holds for the packed spectrum as it
+// stands -- no separation of the two spectra, no real/complex (un)tangling: one forward and three
+// "inverse" W-point complex transforms per PAIR (inverse = forward transform of the conjugate; only
+// max|Re|, max|Im| of the outputs are needed, so the conjugation of the result is irrelevant and the
+// last stage of every inverse transform stays in registers).  Each frame is first scaled to unit
+// sample peak, so a quiet frame is not polluted by the fp32 rounding noise of a loud neighbour, and
+// an all-zero frame returns -100 exactly as the reference does.
 //
 // A polyphase FIR cannot meet the 0.05 dBTP parity bar against this reference.
 #pragma once
@@ -25,12 +33,15 @@ struct TruePeakArgs {
     int n_ch;
     int n_frames;
     int first_frame;           // frames before this are not measured (tp_out untouched)
-    int rounds;
+    int rounds;                // frame pairs per 128-thread group
     const float* window;       // [W] float32 Hann (hop mode) or nullptr
-    const float2* twM;         // [M]
-    const float2* twN;         // [M/2+1]  exp(-2 pi i k / W)
-    const float2* tw4W;        // [3M+1]   exp(+2 pi i j / (4W))
+    const float2* twM;         // [W]      exp(-2 pi i e / W)
+    const float2* rot;         // [3][W]   R_p[k], p = 1..3 (see above)
     double* tp_out;            // [n_ch][n_frames] dBTP
+    // R_p[t + j W/16] = R_p[t] * step[p-1][j]:  step = e^{+2 pi i p j'/64}, j' = j (j < 8) or j - 16 (signed frequency);
+    // uniform constant-bank operands instead of 48 table loads per thread and pair
+    float2 step[3][16];
+    float nyq[3];              // cos(pi p / 4): factor of the bin k = W/2
 };
 
 template <int LOG2M>
@@ -38,29 +49,25 @@ __global__ void __launch_bounds__(256, 2)
 truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
     using S = FftShape<LOG2M>;
     constexpr int M = S::M, TPF = S::TPF, CONC = S::CONC, BUF = S::BUF;
-    constexpr int WARPS_PER_FFT = (TPF + 31) / 32;
-    static_assert(TPF >= 32 && S::NT == 256 && LOG2M <= 12, "true-peak kernel: whole warps per sub-FFT, local FFT variant");
+    constexpr int WARPS = TPF / 32;
+    static_assert(TPF >= 32 && S::NT == 256 && LOG2M <= 12, "true-peak kernel: whole warps per transform, local FFT variant");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufs = reinterpret_cast<float2*>(smem_raw);                            // [CONC][BUF + M]
-    float2* xs_all = bufs + (size_t)CONC * (BUF + M);                              // [CONC][M+1] spectrum
-    float* red_all = reinterpret_cast<float*>(xs_all + (size_t)CONC * (M + 1));   // [CONC][WARPS_PER_FFT]
+    float2* red_all = bufs + (size_t)CONC * (BUF + M);                             // [CONC][2][WARPS] (a, b) maxima
 
     const int tid = threadIdx.x;
     const int g = tid / TPF;
     const int t = tid % TPF;
     float2* X = bufs + (size_t)g * (BUF + M);
     float2* Z = X + BUF;
-    float2* Xs = xs_all + (size_t)g * (M + 1);
-    float* red = red_all + g * WARPS_PER_FFT;
+    float2* red = red_all + g * 2 * WARPS;
 
-    const int frames_per_cta = a.rounds * CONC;
-    const int tiles_per_ch = (a.n_frames + frames_per_cta - 1) / frames_per_cta;
+    const int pairs_per_cta = a.rounds * CONC;
+    const int n_pairs = (a.n_frames + 1) >> 1;
+    const int tiles_per_ch = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
     const int ch = blockIdx.x / tiles_per_ch;
     const int tile = blockIdx.x % tiles_per_ch;
-    const int f0 = tile * frames_per_cta;
 
-    // all 2 x 15 stage twiddles live in registers (four transforms per frame reuse them); the window is
-    // re-read from L1 once per frame instead
     LocalTwFull<LOG2M> st;
     {
         LocalTw<LOG2M> st4;
@@ -69,109 +76,111 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
     }
     const float inv_m = 1.0f / (float)M;
     auto nop = []() {};
-
-    for (int r = 0; r < a.rounds; ++r) {
-        const int f = f0 + r * CONC + g;
-        const bool active = (f < a.n_frames) && (f >= a.first_frame);
-        float2 v[16];
-        float pk = 0.f;                                   // phase 0: the frame itself
-        if (active) {
-            const long long off = (long long)ch * a.ch_stride + a.frame_off0 + (long long)f * a.frame_stride;
-            if (a.x_is_f64) {
-                const double2* px = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(a.x) + off);
+    // group-wide maximum of a float2 (component-wise); every thread of the group gets the result
+    auto group_max2 = [&](float2 v, int slot) -> float2 {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { double2 d = px[t + j * TPF]; v[j] = make_float2((float)d.x, (float)d.y); }
-            } else {
-                const float2* px = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.x) + off);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 w = a.window ? __ldg(reinterpret_cast<const float2*>(a.window) + t + j * TPF) : make_float2(1.f, 1.f);
-                v[j].x *= w.x; v[j].y *= w.y;
-                pk = fmaxf(pk, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x = fmaxf(v.x, __shfl_xor_sync(0xffffffffu, v.x, o));
+            v.y = fmaxf(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
         }
-        fft_forward_local<LOG2M, false>(v, X, Z, st, t, g, active, nop);
-        // untangle -> X[0..M] in Xs
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                int u = (i < 8) ? t + i * TPF : M / 2;
-                if (i == 8 && t != 0) break;
-                float2 Zk = Z[zaddr<LOG2M>(u)];
-                float2 Zm = Z[zaddr<LOG2M>((M - u) & (M - 1))];
-                float2 Xk, Xm;
-                rfft_pair(Zk, Zm, __ldg(a.twN + u), Xk, Xm);
-                Xs[u] = Xk;
-                Xs[M - u] = Xm;
-            }
-        }
+        if ((t & 31) == 0) red[slot * WARPS + (t >> 5)] = v;
         group_sync<TPF>(g);
-        float pko = 0.f;                                  // phases 1..3, unnormalised (x M)
+        float2 m = red[slot * WARPS];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) { const float2 o = red[slot * WARPS + w]; m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); }
+        return m;
+    };
+
+    // this thread's base delay factors R_p[t]
+    const float2 rbase1 = __ldg(a.rot + t), rbase2 = __ldg(a.rot + M + t), rbase3 = __ldg(a.rot + 2 * M + t);
+    // raw samples of a pair: v[j] = (a[t + j TPF], b[t + j TPF]); fetched one round ahead
+    auto load_pair = [&](int pi, float2 (&v)[16]) {
+        const int fa = 2 * pi, fb = fa + 1;
+        const bool act_a = (fa < a.n_frames) && (fa >= a.first_frame);
+        const bool act_b = (fb < a.n_frames) && (fb >= a.first_frame);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+        if (!(act_a || act_b)) return;
+        const long long off_a = (long long)ch * a.ch_stride + a.frame_off0 + (long long)fa * a.frame_stride;
+        const long long off_b = off_a + a.frame_stride;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = t + j * TPF;
+            if (a.x_is_f64) {
+                const double* px = reinterpret_cast<const double*>(a.x);
+                if (act_a) v[j].x = (float)px[off_a + n];
+                if (act_b) v[j].y = (float)px[off_b + n];
+            } else {
+                const float* px = reinterpret_cast<const float*>(a.x);
+                if (act_a) v[j].x = __ldg(px + off_a + n);
+                if (act_b) v[j].y = __ldg(px + off_b + n);
+            }
+        }
+    };
+    float2 v[16];
+    load_pair(tile * pairs_per_cta + g, v);
+    for (int r = 0; r < a.rounds; ++r) {
+        const int pi = tile * pairs_per_cta + r * CONC + g;
+        const int fa = 2 * pi, fb = fa + 1;
+        const bool act_a = (fa < a.n_frames) && (fa >= a.first_frame);
+        const bool act_b = (fb < a.n_frames) && (fb >= a.first_frame);
+        const bool active = act_a || act_b;
+        if (a.window) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float w = __ldg(a.window + t + j * TPF); v[j].x *= w; v[j].y *= w; }
+        }
+        // phase 0 = the frames themselves; scale each to unit sample peak
+        float2 pk = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { pk.x = fmaxf(pk.x, fabsf(v[j].x)); pk.y = fmaxf(pk.y, fabsf(v[j].y)); }
+        pk = group_max2(pk, 0);
+        const float sa = pk.x > 0.f ? 1.f / pk.x : 0.f, sb = pk.y > 0.f ? 1.f / pk.y : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j].x *= sa; v[j].y *= sb; }
+        fft_forward_local<LOG2M, false>(v, X, Z, st, t, g, active, nop);          // ends with a group barrier
+        float2 pko = make_float2(0.f, 0.f);                       // phases 1..3, scaled by M
 #pragma unroll 1
         for (int p = 1; p <= 3; ++p) {
             if (active) {
-                // e^{i pi p/4}
-                const float rr = 0.70710678118654752440f;
-                const float2 cp = (p == 1) ? make_float2(rr, rr) : (p == 2) ? make_float2(0.f, 1.f) : make_float2(-rr, rr);
-                const float cosp = (p == 2) ? 0.f : (p == 1 ? rr : -rr);
-                // Build c[k] = conj(Z'[k]) for the inverse transform, pair (k, M-k) at a time.
-                //   A = Xp[k], B = Xp[M-k];  E = (A + conj B)/2;  O = (A - conj B)/2 * e^{+2 pi i k/W}
-                //   Z'[k] = E + iO, Z'[M-k] = conj(E) + i conj(O)  ->  c[k] = conj(E) - i conj(O), c[M-k] = E - iO
+                const float2 rb = (p == 1) ? rbase1 : (p == 2 ? rbase2 : rbase3);
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    int u = (i < 8) ? t + i * TPF : M / 2;
-                    if (i == 8 && t != 0) break;
-                    float2 A = Xs[u];
-                    float2 B = Xs[M - u];
-                    float2 P = __ldg(a.tw4W + u * p);                 // e^{+2 pi i u p/(4W)}
-                    A = cmul(A, P);
-                    if (u == 0) B = make_float2(B.x * cosp, 0.f);     // Nyquist bin of the W-point spectrum
-                    else B = cmul(B, cmul(cp, make_float2(P.x, -P.y)));
-                    float2 tw = __ldg(a.twN + u);                     // e^{-2 pi i u/W}; conj -> e^{+...}
-                    float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
-                    float2 H = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
-                    float2 O = cmul(H, make_float2(tw.x, -tw.y));
-                    // c[k] = conj(E) - i conj(O) = (E.x - O.y, -E.y - O.x);  c[M-k] = E - iO = (E.x + O.y, E.y - O.x)
-                    Z[zaddr<LOG2M>(u)] = make_float2(E.x - O.y, -E.y - O.x);
-                    if (u != 0) Z[zaddr<LOG2M>(M - u)] = make_float2(E.x + O.y, E.y - O.x);
+                for (int j = 0; j < 16; ++j) {
+                    const int k = t + j * TPF;
+                    float2 rk = cmul(rb, a.step[p - 1][j]);
+                    if (j == 8 && t == 0) rk = make_float2(a.nyq[p - 1], 0.f);      // k = W/2
+                    const float2 s = cmul(Z[zaddr<LOG2M>(k)], rk);
+                    v[j] = make_float2(s.x, -s.y);                // conj: inverse transform by the forward kernel
                 }
-            }
-            group_sync<TPF>(g);      // c[] complete; also: every thread is past the previous transform's X reads
-            if (active) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = Z[zaddr<LOG2M>(t + j * TPF)];
             }
             fft_forward_local<LOG2M, true>(v, X, Z, st, t, g, active, nop);
             if (active) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pko = fmaxf(pko, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
+                for (int j = 0; j < 16; ++j) { pko.x = fmaxf(pko.x, fabsf(v[j].x)); pko.y = fmaxf(pko.y, fabsf(v[j].y)); }
+            }
+            group_sync<TPF>(g);      // every thread is past this transform's X reads before the next stage-1 store
+        }
+        // the next round's samples travel while the maxima are reduced and written
+        if (r + 1 < a.rounds) load_pair(tile * pairs_per_cta + (r + 1) * CONC + g, v);
+        pko = group_max2(pko, 1);
+        if (t == 0) {
+            const float na = fmaxf(1.f, pko.x * inv_m), nb = fmaxf(1.f, pko.y * inv_m);   // normalised peaks (phase 0 = 1)
+            if (act_a) {
+                const double peak = (double)pk.x * (double)na;
+                a.tp_out[(size_t)ch * a.n_frames + fa] = (peak < 1e-10) ? -100.0 : 20.0 * log10(peak);
+            }
+            if (act_b) {
+                const double peak = (double)pk.y * (double)nb;
+                a.tp_out[(size_t)ch * a.n_frames + fb] = (peak < 1e-10) ? -100.0 : 20.0 * log10(peak);
             }
         }
-        pk = fmaxf(pk, pko * inv_m);
-        // reduce over the sub-FFT's threads
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
-        if ((t & 31) == 0) red[t >> 5] = pk;
-        group_sync<TPF>(g);          // also orders the last transform's X reads before the next round's stage-1 store
-        if (active && t == 0) {
-            float m = red[0];
-#pragma unroll
-            for (int w = 1; w < WARPS_PER_FFT; ++w) m = fmaxf(m, red[w]);
-            double peak = (double)m;
-            a.tp_out[(size_t)ch * a.n_frames + f] = (peak < 1e-10) ? -100.0 : 20.0 * log10(peak);
-        }
-        // red[] is next written after several barriers of the next round
+        group_sync<TPF>(g);          // red[] and Z are reused by the next round
     }
 }
 
 template <int LOG2M>
 inline size_t truepeak_smem_bytes() {
     using S = FftShape<LOG2M>;
-    return (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) + (size_t)S::CONC * (S::M + 1) * sizeof(float2)
-           + (size_t)S::CONC * ((S::TPF + 31) / 32) * sizeof(float) + 16;
+    return (size_t)S::CONC * (S::BUF + S::M) * sizeof(float2) + (size_t)S::CONC * 2 * (S::TPF / 32) * sizeof(float2) + 16;
 }
 
 }  // namespace o4

@@ -705,7 +705,10 @@ def test_batch_driver_tiles_match_one_shot_and_oracle(plan):
         met_t[:, k:k + nh] = m
         k += nh
     torch.cuda.synchronize()
-    assert k == n_hops and torch.equal(comb_t, comb) and torch.equal(met_t, met)
+    # spectra and LUFS columns are bit-identical; the true-peak kernel packs two consecutive frames into
+    # one complex transform, so a different tiling pairs frames differently: same value to fp32 rounding
+    assert k == n_hops and torch.equal(comb_t, comb) and torch.equal(met_t[..., :4], met[..., :4])
+    assert float((met_t[..., 4] - met[..., 4]).abs().max()) < 1e-4
     # channels are independent: a single channel run alone gives the same rows
     solo = plan.analyze_host(x[4:5])
     assert np.array_equal(solo["combined"][0], host["combined"][4]) and np.array_equal(solo["meters"][0], host["meters"][4])
