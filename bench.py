@@ -36,7 +36,8 @@ UNIT = "stream-s/s"
 SR, HOP, T_BINS, CHANNELS = 48000, 512, 512, 2
 B_ALG_PER_HOP = 2048 + 2048 + 20          # SURVEY.md section 8d, fused-output mode: 512 f32 in, 512 f32 + 5 f32 out
 FLOP_PER_HOP = 0.9e6                      # SURVEY.md section 8d estimate (fp32 + the fp64 biquads)
-FP32_PEAK_TFLOPS = 75.0                   # nominal B200 CUDA-core fp32 (not in MEASURED_PEAKS.json)
+FP32_PEAK_TFLOPS = 70.8                   # measured FFMA peak on this pool's B200 (profiles/r01_fp_pipes_microbench.txt:
+                                          # 121.7 lanes/clk/SM x 148 SMs x 1.965 GHz x 2); nominal 75
 
 
 def measured_peaks():
@@ -318,12 +319,14 @@ def main():
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "peak_source": peak_kind, "kernel_ms": ktimes[dom],
                     "kernel_share_of_step": ktimes[dom] / sum(ktimes.values()),
-                    "note": "fp32-issue bound by arithmetic (about 220 FLOP per compulsory byte): low HBM fraction is expected"}
+                    "note": "fp32-issue bound by arithmetic (about 220 FLOP per compulsory byte): low HBM fraction is expected; "
+                            "kernel_share_of_step is of the summed kernel times (the statistics kernel overlaps the FFT kernels)"}
         pipe_gbs = ch_hops * B_ALG_PER_HOP / (ms_per_step / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (FFT, combine) + f64 (K-weighting biquads, meter statistics)", "data": "synthetic",
+            "dtype": "f32 (FFT, combine; 3xTF32 tensor-core GEMM for the few-bin resolutions) + f64 (K-weighting biquads, meter statistics)",
+            "data": "synthetic",
             "config": {"workload": f"BASELINE config[2]: {n_streams} stereo streams x {args.seconds} s @48 kHz per GPU, "
                                    "4 resolutions 8192/4096/2048/1024, hop 512, 512 target bins (fused output mode B), "
                                    "LUFS M/S/I/LRA + 4x true peak per hop",
@@ -333,7 +336,7 @@ def main():
             "roofline": roof,
             "pipeline_hbm": {"algorithmic_bytes_per_channel_hop": B_ALG_PER_HOP, "achieved_gbs": pipe_gbs, "frac": pipe_gbs / hbm_peak},
             "roofline_fp32": {"flop_per_channel_hop": FLOP_PER_HOP, "achieved_tflops": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12,
-                              "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                              "peak_tflops_measured": FP32_PEAK_TFLOPS,
                               "frac": ch_hops * FLOP_PER_HOP / (ms_per_step / 1e3) / 1e12 / FP32_PEAK_TFLOPS},
             "kernel_ms": ktimes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "next_rows": next_rows,
             "final_rows_checksum": checksum,
