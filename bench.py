@@ -140,6 +140,10 @@ def main():
                     help="streams per host-buffer call of the e2e leg (halved until the pinned buffers can be allocated)")
     ap.add_argument("--cpu-seconds", type=float, default=60.0,
                     help="seconds per stream of the CPU baseline sample (one stream per host core; 60 s = the workload's stream length)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 (default, the metric's configuration): 48 kHz stereo, 8192/4096/2048/1024; "
+                         "config5: 96 kHz 8-channel (7.1) streams, six resolutions 32768 .. 1024 (BASELINE configs[4] shape; "
+                         "an extra workload, reported with its own config.workload string)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -155,7 +159,7 @@ def main():
     import torch
     import torch.distributed as dist
     from omega4_b200 import _native as N
-    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS, CONFIG5_96K
     from omega4_b200.batch.driver import device_synth
     from omega4_b200.batch.partition import gather_rows, final_rows
 
@@ -167,10 +171,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    global SR, CHANNELS
+    configs, wl_name = BASELINE_CONFIGS, "BASELINE config[2]"
+    if args.workload == "config5":
+        SR, CHANNELS, configs, wl_name = 96000, 8, CONFIG5_96K, "BASELINE configs[4] shape (96 kHz, 8 channels, 6 resolutions)"
+        args.no_cpu = True                       # the CPU leg times the metric's configuration only
     n_streams, n_ch = args.streams, args.streams * CHANNELS
     n_hops = args.seconds * SR // HOP
     n_samples = n_hops * HOP
-    plan = AnalysisPlan(SR, BASELINE_CONFIGS, T_BINS, device=local)
+    plan = AnalysisPlan(SR, configs, T_BINS, device=local)
     first_stream = rank * n_streams
     x = device_synth(n_streams, CHANNELS, n_samples, SR, first_stream=first_stream, device=local)
     comb = torch.empty((n_ch, n_hops, T_BINS), dtype=torch.float32, device=dev)
@@ -222,6 +231,8 @@ def main():
     next_rows = {}
     try:
         from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+        if args.workload != "config2":
+            raise RuntimeError("timed for the metric's configuration only")
         post = SpectrumPostProcessor(T_BINS, SR, 2048, device=local)
         post._ensure()
         bars = torch.empty((n_ch, n_hops, post.n_valid), dtype=torch.float32, device=dev)
@@ -323,12 +334,13 @@ def main():
                             "kernel_share_of_step is of the summed kernel times (the statistics kernel overlaps the FFT kernels)"}
         pipe_gbs = ch_hops * B_ALG_PER_HOP / (ms_per_step / 1e3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.workload == "config2" else METRIC.replace("48 kHz stereo", "96 kHz 8-channel"),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (FFT, combine; 3xTF32 tensor-core GEMM for the few-bin resolutions) + f64 (K-weighting biquads, meter statistics)",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE config[2]: {n_streams} stereo streams x {args.seconds} s @48 kHz per GPU, "
-                                   "4 resolutions 8192/4096/2048/1024, hop 512, 512 target bins (fused output mode B), "
+            "config": {"workload": f"{wl_name}: {n_streams} streams x {CHANNELS} ch x {args.seconds} s @{SR // 1000} kHz per GPU, "
+                                   f"resolutions {'/'.join(str(c[1]) for c in configs)}, hop 512, 512 target bins (fused output mode B), "
                                    "LUFS M/S/I/LRA + 4x true peak per hop",
                        "streams_per_gpu": n_streams, "seconds": args.seconds, "channels": CHANNELS,
                        "channel_hops_per_step_per_gpu": ch_hops, "parallelism": f"streams sharded x{world}, no data-path collective",
