@@ -99,6 +99,66 @@ __global__ void s16_deinterleave_kernel(const int16_t* __restrict__ in, long lon
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BassZoomPanel._process_bass_detail_internal (omega4/panels/bass_zoom.py:141-214), data side without the
+// wall-clock peak hold:  raw = mean(|X|[bins of the bar]) * comp[bar];  scale = 0.85 / max(raw) *
+// log10(max(1, 10 max(raw))) / 2;  v = raw * scale, compressed above 0.7 (0.7 + 0.3 (v - 0.7));  attack /
+// release smoothing against the previous bars (0.1/0.9 when rising, 0.6/0.4 when falling);  clamp [0, 1].
+// One warp per channel walks its frames in order (the smoothing is the only sequential dependency).
+// ---------------------------------------------------------------------------------------------
+__global__ void bass_bars_kernel(const float* __restrict__ mag, int n_ch, int n_frames, int n_bins,
+                                 const int* __restrict__ bar_bins, const float* __restrict__ comp, int n_bars,
+                                 float* __restrict__ state, float* __restrict__ out) {
+    const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (ch >= n_ch) return;
+    constexpr int MAXB = 4;                                    // up to 128 bars
+    float prev[MAXB];
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) { const int b = lane + 32 * i; prev[i] = (state && b < n_bars) ? state[(size_t)ch * n_bars + b] : 0.f; }
+    for (int f = 0; f < n_frames; ++f) {
+        const float* row = mag + ((size_t)ch * n_frames + f) * n_bins;
+        float raw[MAXB];
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+            const int b = lane + 32 * i;
+            raw[i] = -1.f;                                     // bars without bins keep their value (:163, :200)
+            if (b < n_bars) {
+                const int s = bar_bins[2 * b], n = bar_bins[2 * b + 1];
+                if (n > 0) {
+                    float acc = 0.f;
+                    for (int k = 0; k < n; ++k) acc += row[s + k];
+                    raw[i] = (acc / (float)n) * comp[b];
+                    mx = fmaxf(mx, raw[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float scale = mx > 0.f ? (0.85f / mx) * (log10f(fmaxf(1.0f, mx * 10.f)) * 0.5f) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+            const int b = lane + 32 * i;
+            if (b < n_bars) {
+                float v = prev[i];
+                if (raw[i] >= 0.f) {
+                    const float sv = raw[i] * scale;
+                    const float cv = sv > 0.7f ? 0.7f + (sv - 0.7f) * 0.3f : sv;
+                    v = (cv > v) ? v * 0.1f + cv * 0.9f : v * 0.6f + cv * 0.4f;
+                    v = fmaxf(0.f, fminf(1.f, v));
+                }
+                prev[i] = v;
+                out[((size_t)ch * n_frames + f) * n_bars + b] = v;
+            }
+        }
+    }
+    if (state) {
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) { const int b = lane + 32 * i; if (b < n_bars) state[(size_t)ch * n_bars + b] = prev[i]; }
+    }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     return h;

@@ -1348,6 +1348,54 @@ extern "C" int omega4_band_map(int device, void* stream, int mem, const float* s
     return OMEGA4_OK;
 }
 
+extern "C" int omega4_bass_bars(int device, void* stream, int mem, const float* magnitudes, int n_ch, int n_frames,
+                                int n_bins, const int* bar_bins, const float* comp, int n_bars, float* state,
+                                float* bars_out) {
+    if (!magnitudes || !bar_bins || !comp || !bars_out || n_ch < 0 || n_frames < 0 || n_bins <= 0 || n_bars <= 0 || n_bars > 128)
+        return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_ch == 0 || n_frames == 0) return OMEGA4_OK;
+    for (int b = 0; b < n_bars; ++b)
+        if (bar_bins[2 * b] < 0 || bar_bins[2 * b + 1] < 0 || bar_bins[2 * b] + bar_bins[2 * b + 1] > n_bins)
+            return fail(OMEGA4_ERR_INVALID, "bar bins out of range");
+    if (omega4_device_count() == 0) return fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<void*> to_free;
+    auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
+#define CKF(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(OMEGA4_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(e__)); } } while (0)
+    int* d_bins = nullptr; float* d_comp = nullptr;
+    CKF(cudaMalloc(&d_bins, (size_t)n_bars * 2 * sizeof(int))); to_free.push_back(d_bins);
+    CKF(cudaMalloc(&d_comp, (size_t)n_bars * sizeof(float))); to_free.push_back(d_comp);
+    CKF(cudaMemcpyAsync(d_bins, bar_bins, (size_t)n_bars * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CKF(cudaMemcpyAsync(d_comp, comp, (size_t)n_bars * sizeof(float), cudaMemcpyHostToDevice, s));
+    const float* d_mag = magnitudes; float* d_out = bars_out; float* d_state = state;
+    const size_t rows = (size_t)n_ch * n_frames;
+    if (mem == OMEGA4_MEM_HOST) {
+        float* t = nullptr;
+        CKF(cudaMalloc(&t, rows * n_bins * sizeof(float))); to_free.push_back(t);
+        CKF(cudaMemcpyAsync(t, magnitudes, rows * n_bins * sizeof(float), cudaMemcpyHostToDevice, s));
+        d_mag = t;
+        CKF(cudaMalloc(&d_out, rows * n_bars * sizeof(float))); to_free.push_back(d_out);
+        if (state) {
+            CKF(cudaMalloc(&d_state, (size_t)n_ch * n_bars * sizeof(float))); to_free.push_back(d_state);
+            CKF(cudaMemcpyAsync(d_state, state, (size_t)n_ch * n_bars * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+    } else if (mem != OMEGA4_MEM_DEVICE) {
+        cleanup();
+        return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
+    }
+    bass_bars_kernel<<<(unsigned)((n_ch + 3) / 4), 128, 0, s>>>(d_mag, n_ch, n_frames, n_bins, d_bins, d_comp, n_bars, d_state, d_out);
+    CKF(cudaGetLastError());
+    if (mem == OMEGA4_MEM_HOST) {
+        CKF(cudaMemcpyAsync(bars_out, d_out, rows * n_bars * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (state) CKF(cudaMemcpyAsync(state, d_state, (size_t)n_ch * n_bars * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CKF(cudaStreamSynchronize(s));
+    cleanup();
+#undef CKF
+    return OMEGA4_OK;
+}
+
 extern "C" int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams, int n_channels,
                                  long long n_samples, long long row_stride, int first_stream, int sample_rate,
                                  long long clip_samples) {

@@ -37,7 +37,7 @@ EXPORTS = (
     "omega4_plan_create", "omega4_plan_destroy", "omega4_analyze", "omega4_combine",
     "omega4_meter_frames", "omega4_meter_stats", "omega4_rfft_batch", "omega4_band_map",
     "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
-    "omega4_analyze_s16", "omega4_plan_set_weighting", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
+    "omega4_analyze_s16", "omega4_plan_set_weighting", "omega4_bass_bars", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
 )
 
 
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         l.omega4_rfft_batch.argtypes = [ip, vp, ip, vp, ip, ip, vp, vp, vp]
         l.omega4_band_map.restype = ip
         l.omega4_band_map.argtypes = [ip, vp, ip, vp, ip, ip, vp, ip, vp, vp, ip]
+        l.omega4_bass_bars.restype = ip
+        l.omega4_bass_bars.argtypes = [ip, vp, ip, vp, ip, ip, ip, vp, vp, ip, vp, vp]
         l.omega4_synth_fill.restype = ip
         l.omega4_synth_fill.argtypes = [ip, vp, vp, ip, ip, ll, ll, ip, ip, ll]
         l.omega4_plan_launches.restype = ll

@@ -171,6 +171,15 @@ int omega4_rfft_batch(int device, void* stream, int mem, const float* frames, in
 int omega4_band_map(int device, void* stream, int mem, const float* spectrum, int n_rows, int len,
                     const int* bands, int n_bars, const float* comp, float* bars_out, int db);
 
+/* BassZoomPanel._process_bass_detail_internal (omega4/panels/bass_zoom.py:141-214) after its 8192-point
+ * FFT (omega4_rfft_batch), without the wall-clock peak hold: per bar mean(|X|[first .. first+count)) * comp,
+ * dynamic scaling 0.85/max * log10(max(1, 10 max))/2, compression above 0.7, attack/release smoothing
+ * against the previous bars, clamp [0,1].  magnitudes [n_ch][n_frames][n_bins]; bar_bins [n_bars][2]
+ * (first bin, count; count 0 = bar keeps its value) and comp [n_bars] are HOST tables; state
+ * [n_ch][n_bars] carries bass_bar_values between calls (NULL: zeros); bars_out [n_ch][n_frames][n_bars]. */
+int omega4_bass_bars(int device, void* stream, int mem, const float* magnitudes, int n_ch, int n_frames,
+                     int n_bins, const int* bar_bins, const float* comp, int n_bars, float* state, float* bars_out);
+
 /* Device-side synthetic multi-stream audio for the headless batch driver (sweep + counter-hash noise). */
 int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams, int n_channels,
                       long long n_samples, long long row_stride, int first_stream, int sample_rate,

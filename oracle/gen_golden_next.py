@@ -14,7 +14,7 @@ the UNMODIFIED reference in the build container (needs /root/reference):
   band table included).
 * meters_weighting.npz -- ProfessionalMetering.apply_a_weighting / apply_c_weighting / Z mode and
   calculate_lufs in those modes (professional_meters.py:74-127, 155-229).
-* wire_formats.npz -- AudioCaptureManager's s16le / float32le chunk decoding (omega4/audio/capture.py:549-574).
+* bass_zoom.npz -- BassZoomPanel._process_bass_detail_internal bar values (omega4/panels/bass_zoom.py:141-214).
 """
 import inspect
 import os
@@ -54,6 +54,7 @@ import omega4_main  # noqa: E402
 from omega4.audio.multi_resolution_fft import MultiResolutionFFT, FFTConfig, WindowType  # noqa: E402
 from omega4.optimization.freq_mapper import PrecomputedFrequencyMapper  # noqa: E402
 from omega4.panels.professional_meters import ProfessionalMetering  # noqa: E402
+from omega4.panels.bass_zoom import BassZoomPanel  # noqa: E402
 from omega4_b200.batch.synth import synth_channel  # noqa: E402
 
 HOP, W = 512, 2048
@@ -146,14 +147,47 @@ def gen_meter_weighting():
     np.savez_compressed(os.path.join(OUT, "meters_weighting.npz"), **out)
 
 
+def gen_bass_zoom():
+    """BassZoomPanel._process_bass_detail_internal on the app's Hann-windowed 2048-sample frames
+    (omega4_main.py:1197), bar values only (the peak hold is wall-clock driven)."""
+    sr = 48000
+    x = synth_channel(2, 0, 60 * HOP, sr)
+    x[30 * HOP:34 * HOP] = 0.0
+    panel = BassZoomPanel(sr)
+    panel.bass_thread_running = False                      # the worker thread is not used
+    frames, bars = [], []
+    for k in range(3, 60):
+        fr = x[(k + 1) * HOP - W:(k + 1) * HOP] * np.hanning(W)
+        res = panel._process_bass_detail_internal(fr)
+        panel.bass_bar_values = res["bar_values"]
+        frames.append(fr.astype(np.float32))
+        bars.append(np.array(res["bar_values"], dtype=np.float64))
+    # the reference computes on the float64 frame; the fixture stores float32 frames (what the GPU path is fed)
+    # and re-runs the reference on exactly those so that input and output belong together
+    panel2 = BassZoomPanel(sr)
+    panel2.bass_thread_running = False
+    bars32 = []
+    for fr in frames:
+        res = panel2._process_bass_detail_internal(fr.astype(np.float64))
+        panel2.bass_bar_values = res["bar_values"]
+        bars32.append(np.array(res["bar_values"], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, "bass_zoom.npz"), frames=np.stack(frames), bars=np.stack(bars32),
+                        n_bars=panel.bass_detail_bars,
+                        bin_first=np.array([g[0] for g in panel.bass_bin_mapping], dtype=np.int32),
+                        bin_count=np.array([len(g) for g in panel.bass_bin_mapping], dtype=np.int32),
+                        ranges=np.array(panel.bass_freq_ranges, dtype=np.float64))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["app_post", "meter_weighting"]
+    which = sys.argv[1:] or ["app_post", "meter_weighting", "bass_zoom"]
     if "app_post" in which:
         gen_app_post()
     if "meter_weighting" in which:
         gen_meter_weighting()
-    for f in ("app_post.npz", "meters_weighting.npz"):
+    if "bass_zoom" in which:
+        gen_bass_zoom()
+    for f in ("app_post.npz", "meters_weighting.npz", "bass_zoom.npz"):
         pth = os.path.join(OUT, f)
         if os.path.exists(pth):
             print(f, os.path.getsize(pth))

@@ -517,6 +517,57 @@ class OracleSpectrumPost:
 
 
 # --------------------------------------------------------------------------------------
+# bass zoom panel, data side (omega4/panels/bass_zoom.py) -- SURVEY.md section 8f rank 3
+# --------------------------------------------------------------------------------------
+def bass_mapping(sample_rate: int = 48000, fft_size: int = 8192):
+    """setup_bass_mapping (bass_zoom.py:50-97) -> (freq_ranges, bin groups)."""
+    freqs = np.fft.rfftfreq(fft_size, 1 / sample_rate)
+    valid = [i for i, f in enumerate(freqs) if 20 <= f <= 200]
+    ranges, groups = [], []
+    per = max(1, len(valid) // 31)
+    for i in range(0, len(valid), per):
+        g = valid[i:min(i + per, len(valid))]
+        if g:
+            f0, f1 = freqs[g[0]], freqs[g[-1]]
+            if ranges:
+                f0 = max(f0, ranges[-1][1])
+            ranges.append((f0, f1))
+            groups.append(g)
+    return ranges, groups
+
+
+def bass_bars_step(audio, bar_values, ranges, groups, fft_size: int = 8192) -> np.ndarray:
+    """_process_bass_detail_internal (bass_zoom.py:141-214) without the wall-clock peak hold:
+    returns the new bar values (float32, like the reference's array)."""
+    audio = np.asarray(audio)
+    window = np.hanning(min(len(audio), fft_size))
+    if len(audio) < fft_size:
+        padded = np.zeros(fft_size)
+        padded[:len(audio)] = audio * window
+    else:
+        padded = audio[:fft_size] * window
+    mag = np.abs(np.fft.rfft(padded))
+    bars = np.array(bar_values, dtype=np.float32).copy()
+    raw, mx = {}, 0.0
+    for i, g in enumerate(groups):
+        if i >= len(bars):
+            break
+        if len(g) > 0:
+            v = np.mean(mag[g])
+            c = (ranges[i][0] + ranges[i][1]) / 2
+            v *= 0.3 if c < 60 else 0.6 if c < 100 else 1.0 if c < 150 else 0.8
+            raw[i] = v
+            mx = max(mx, v)
+    scale = (0.85 / mx) * (np.log10(max(1.0, mx * 10)) / 2.0) if mx > 0 else 1.0
+    for i in raw:
+        sv = raw[i] * scale
+        cv = 0.7 + (sv - 0.7) * 0.3 if sv > 0.7 else sv
+        bars[i] = bars[i] * 0.1 + cv * 0.9 if cv > bars[i] else bars[i] * 0.6 + cv * 0.4
+        bars[i] = max(0.0, min(1.0, bars[i]))
+    return bars
+
+
+# --------------------------------------------------------------------------------------
 # professional meters (omega4/panels/professional_meters.py)
 # --------------------------------------------------------------------------------------
 def butter2_highpass(fc: float, fs: float):

@@ -443,6 +443,34 @@ def test_new_entry_points_reject_bad_arguments(plan):
     post.close()
 
 
+# ------------------------------------------------------------------ section 8f rank 3: bass zoom panel data side
+def test_bass_zoom_panel_golden(golden):
+    """BassZoomPanel._process_bass_detail_internal (bass_zoom.py:141-214): Hann + zero-padded 8192-point
+    rFFT (omega4_rfft_batch) and bar mean / compensation / dynamic scaling / compression / smoothing
+    (omega4_bass_bars) against the reference's own bar values."""
+    from omega4_b200.panels.bass_zoom import BassZoomPanel
+    g = golden("bass_zoom.npz")
+    p = BassZoomPanel(48000)
+    assert p.bass_detail_bars == int(g["n_bars"]) and [x[0] for x in p.bass_bin_mapping] == list(g["bin_first"])
+    np.testing.assert_allclose(np.array(p.bass_freq_ranges), g["ranges"], rtol=0, atol=1e-12)
+    for k, (fr, want) in enumerate(zip(g["frames"], g["bars"])):           # frame at a time, state on the object
+        p.update(fr)
+        assert np.abs(p.bass_bar_values - want).max() <= TOL_BAR, k
+    assert np.all(p.bass_peak_values >= p.bass_bar_values - 1e-6)
+    # batch: all frames in one call, two channels (second one reversed in time), carried state
+    frames = np.stack([g["frames"], g["frames"][::-1]])
+    one = p.bar_values_batch(frames)
+    assert np.abs(one[0] - g["bars"]).max() <= TOL_BAR
+    state = np.zeros((2, p.bass_detail_bars), np.float32)
+    parts = [p.bar_values_batch(frames[:, s:s + 10], state) for s in range(0, frames.shape[1], 10)]
+    assert np.array_equal(np.concatenate(parts, axis=1), one)
+    ranges, groups = O.bass_mapping(48000)
+    bars = np.zeros(len(groups), np.float32)
+    for j, fr in enumerate(frames[1]):
+        bars = O.bass_bars_step(fr.astype(np.float64), bars, ranges, groups)
+        assert np.abs(one[1, j] - bars).max() <= TOL_BAR
+
+
 # ------------------------------------------------------------------ meters
 def test_meters_stream_golden(plan, golden):
     g = golden("meters_stream.npz")

@@ -339,3 +339,16 @@ def test_restated_first_order_filtfilt_matches_scipy():
     x = rng.standard_normal((2, 2048))
     for b, a in O.a_weighting_sections(48000):
         np.testing.assert_allclose(O.filtfilt_any(b, a, x), sps.filtfilt(b, a, x), rtol=0, atol=1e-9)   # 20.6 Hz poles: 1e-11 round-off
+
+
+# ---------------------------------------------------------------- section 8f rank 3: bass zoom panel data side
+def test_bass_zoom_bars_match_reference(golden):
+    g = golden("bass_zoom.npz")
+    ranges, groups = O.bass_mapping(48000)
+    assert len(groups) == int(g["n_bars"]) == 31
+    assert np.array_equal([x[0] for x in groups], g["bin_first"]) and np.array_equal([len(x) for x in groups], g["bin_count"])
+    np.testing.assert_allclose(np.array(ranges), g["ranges"], rtol=0, atol=1e-12)
+    bars = np.zeros(len(groups), np.float32)
+    for fr, want in zip(g["frames"], g["bars"]):
+        bars = O.bass_bars_step(fr.astype(np.float64), bars, ranges, groups)
+        np.testing.assert_allclose(bars, want, rtol=0, atol=1e-7)
