@@ -60,47 +60,6 @@ __device__ __forceinline__ void bf8(float2* v) {
     v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
 
-// first half of the radix-16 butterfly: four radix-4 over j = a + 4b and the internal twiddles
-// W16^{ac}; leaves t[a][c] at v[a + 4c]
-__device__ __forceinline__ void bf16pt_step1(float2* v) {
-    const float c1 = 0.92387953251128675613f;   // cos(pi/8)
-    const float s1 = 0.38268343236508977173f;   // sin(pi/8)
-    const float r = 0.70710678118654752440f;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) bf4(v[a], v[a + 4], v[a + 8], v[a + 12]);
-    v[1 + 4]  = cmul(v[1 + 4],  make_float2(c1, -s1));
-    v[1 + 8]  = make_float2((v[1 + 8].x + v[1 + 8].y) * r, (v[1 + 8].y - v[1 + 8].x) * r);
-    v[1 + 12] = cmul(v[1 + 12], make_float2(s1, -c1));
-    v[2 + 4]  = make_float2((v[2 + 4].x + v[2 + 4].y) * r, (v[2 + 4].y - v[2 + 4].x) * r);
-    v[2 + 8]  = mul_mi(v[2 + 8]);
-    v[2 + 12] = make_float2((v[2 + 12].y - v[2 + 12].x) * r, -(v[2 + 12].x + v[2 + 12].y) * r);
-    v[3 + 4]  = cmul(v[3 + 4],  make_float2(s1, -c1));
-    v[3 + 8]  = make_float2((v[3 + 8].y - v[3 + 8].x) * r, -(v[3 + 8].x + v[3 + 8].y) * r);
-    v[3 + 12] = cmul(v[3 + 12], make_float2(-c1, s1));
-}
-
-// single output d of a forward radix-4: t0 + W4^d t1 + W4^2d t2 + W4^3d t3, W4 = -i
-template <int D>
-__device__ __forceinline__ float2 r4_out(float2 t0, float2 t1, float2 t2, float2 t3) {
-    if (D == 0) return cadd(cadd(t0, t2), cadd(t1, t3));
-    if (D == 2) return csub(cadd(t0, t2), cadd(t1, t3));
-    const float2 b = csub(t0, t2), d = mul_mi(csub(t1, t3));
-    return (D == 1) ? cadd(b, d) : csub(b, d);
-}
-
-// w^K from the four table powers (K is a compile-time constant after unrolling)
-struct Tw4;
-template <int K>
-__device__ __forceinline__ float2 tw_pow(const float2& w1, const float2& w2, const float2& w4, const float2& w8) {
-    float2 acc = make_float2(1.f, 0.f);
-    bool have = false;
-    if (K & 1) { acc = w1; have = true; }
-    if (K & 2) { acc = have ? cmul(acc, w2) : w2; have = true; }
-    if (K & 4) { acc = have ? cmul(acc, w4) : w4; have = true; }
-    if (K & 8) { acc = have ? cmul(acc, w8) : w8; have = true; }
-    return acc;
-}
-
 // forward radix-16 butterfly: out[k] = sum_j in[j] W16^{jk}, in place, natural order out.
 __device__ __forceinline__ void bf16pt(float2* v) {
     const float c1 = 0.92387953251128675613f;   // cos(pi/8)
@@ -407,99 +366,6 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
         }
     }
     if (!KEEP_LAST_IN_REGS) group_sync<TPF>(g);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Output-pruned local transform for the FUSED mode of the low resolutions: when the combine step
-// only needs real-FFT bins u < 256 (e.g. N = 8192 feeds 20-200 Hz = bins 4..35), the untangle
-// only reads Z[u] (stage-3 output pq = 0 of stage-2 outputs k = u >> 4) and Z[M-u] (pq = G2-1 of
-// k' = ((M-u) >> 4) & 15).  Stage 2 then evaluates and exchanges only the stage-2 outputs in
-// kmask = mask_lo | mask_hi, and stage 3 only the listed single outputs (one lane each).
-//   prune_list[j] = k | (type << 4), type 0: pq = 0 (plain sum), type 1: pq = G2-1 (conj roots)
-// ---------------------------------------------------------------------------------------------
-struct PruneSpec {
-    unsigned mask_lo, mask_hi;
-    int n_out;
-    unsigned char list[32];
-};
-
-template <int G2>
-__device__ __forceinline__ float2 conj_root(int pp) {      // conj(W_G2^pp) = exp(+2 pi i pp / G2), pp static
-    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, r = 0.70710678118654752440f;
-    const int e = (pp * (16 / G2)) & 15;                   // exponent on the 16-point circle
-    const float cs[16] = {1.f, c1, r, s1, 0.f, -s1, -r, -c1, -1.f, -c1, -r, -s1, 0.f, s1, r, c1};
-    const float sn[16] = {0.f, s1, r, c1, 1.f, c1, r, s1, 0.f, -s1, -r, -c1, -1.f, -c1, -r, -s1};
-    return make_float2(cs[e], sn[e]);
-}
-
-template <int LOG2M, typename Mid>
-__device__ __forceinline__ void fft_forward_local_pruned(float2* v, float2* X, float2* Z, const LocalTw<LOG2M>& st,
-                                                         int t, int g, bool active, const PruneSpec& ps, Mid&& mid) {
-    constexpr int M = 1 << LOG2M;
-    constexpr int TPF = M / 16;
-    constexpr int G2 = M / 256;
-    constexpr int S = 17 * G2;
-    static_assert(LOG2M >= 10 && LOG2M <= 12, "pruned variant: 1024 .. 4096 complex points");
-    if (active) {
-        bf16pt(v);
-        apply_twiddles(v, st.s1);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) X[k * S + t] = v[k];
-    }
-    group_sync<TPF>(g);
-    mid();
-    if (active) {
-        const int q = t / G2, p = t % G2;
-        float2* Xq = X + q * S;
-        const unsigned kmask = ps.mask_lo | ps.mask_hi;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = Xq[p + G2 * j];
-        bf16pt_step1(v);
-        float2 o[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const unsigned cm = (kmask >> c) & 0x1111u;       // bits 0,4,8,12 <-> d = 0..3 (k = c + 4d)
-            if (cm == 0x1111u) {
-                float2 t0 = v[4 * c], t1 = v[4 * c + 1], t2 = v[4 * c + 2], t3 = v[4 * c + 3];
-                bf4(t0, t1, t2, t3);
-                o[c] = t0; o[c + 4] = t1; o[c + 8] = t2; o[c + 12] = t3;
-            } else {
-                if (cm & 0x0001u) o[c] = r4_out<0>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                if (cm & 0x0010u) o[c + 4] = r4_out<1>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                if (cm & 0x0100u) o[c + 8] = r4_out<2>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                if (cm & 0x1000u) o[c + 12] = r4_out<3>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            }
-        }
-        __syncwarp();                         // every lane of the group holds its inputs in registers
-#define O4_PRUNE_STORE(K)                                                                              \
-        if (kmask & (1u << K)) {                                                                       \
-            float2 val = o[K];                                                                         \
-            if (K > 0) val = cmul(val, tw_pow<K>(st.s2.w1, st.s2.w2, st.s2.w4, st.s2.w8));              \
-            Xq[17 * p + K] = val;                                                                      \
-        }
-        O4_PRUNE_STORE(0) O4_PRUNE_STORE(1) O4_PRUNE_STORE(2) O4_PRUNE_STORE(3)
-        O4_PRUNE_STORE(4) O4_PRUNE_STORE(5) O4_PRUNE_STORE(6) O4_PRUNE_STORE(7)
-        O4_PRUNE_STORE(8) O4_PRUNE_STORE(9) O4_PRUNE_STORE(10) O4_PRUNE_STORE(11)
-        O4_PRUNE_STORE(12) O4_PRUNE_STORE(13) O4_PRUNE_STORE(14) O4_PRUNE_STORE(15)
-#undef O4_PRUNE_STORE
-        __syncwarp();
-        // stage 3: listed single outputs, lane p of the group takes outputs p, p + G2, ...
-        for (int j = p; j < ps.n_out; j += G2) {
-            const int e = ps.list[j];
-            const int k = e & 15;
-            const bool hi = (e >> 4) != 0;
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int pp = 0; pp < G2; ++pp) {
-                const float2 x = Xq[17 * pp + k];
-                const float2 w = conj_root<G2>(pp);
-                const float2 xr = hi ? cmul(x, w) : x;
-                acc = cadd(acc, xr);
-            }
-            Z[zaddr<LOG2M>(q + 16 * k + (hi ? 256 * (G2 - 1) : 0))] = acc;
-        }
-    }
-    group_sync<TPF>(g);
 }
 
 // Untangle one (k, M-k) pair of the packed real transform.

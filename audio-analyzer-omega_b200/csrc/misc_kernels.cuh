@@ -73,11 +73,6 @@ __global__ void band_map_kernel(const float* __restrict__ spec, int n_rows, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Synthetic benchmark audio: log sweep 20 Hz -> 20 kHz over the clip, amplitude 0.5, start phase
-// from the (stream, channel) hash of omega4_b200/batch/synth.py, plus white counter-hash noise of
-// RMS 0.1 (the numpy generator shapes its noise pink; spectral colour is irrelevant to throughput).
-// ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
 // Wire format of the capture side: interleaved little-endian int16 frames ->
 // planar float32 rows,  x = int16 / 32768  (omega4/audio/capture.py:571-574; exact in float32).
 // Stream g, frame i, channel c  ->  out[(g*il + c) * out_stride + i]
@@ -159,6 +154,11 @@ __global__ void bass_bars_kernel(const float* __restrict__ mag, int n_ch, int n_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Synthetic benchmark audio: log sweep 20 Hz -> 20 kHz over the clip, amplitude 0.5, start phase
+// from the (stream, channel) hash of omega4_b200/batch/synth.py, plus white counter-hash noise of
+// RMS 0.1 (the numpy generator shapes its noise pink; spectral colour is irrelevant to throughput).
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     return h;
