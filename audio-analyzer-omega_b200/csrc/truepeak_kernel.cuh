@@ -134,7 +134,9 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { pk.x = fmaxf(pk.x, fabsf(v[j].x)); pk.y = fmaxf(pk.y, fabsf(v[j].y)); }
         pk = group_max2(pk, 0);
-        const float sa = pk.x > 0.f ? 1.f / pk.x : 0.f, sb = pk.y > 0.f ? 1.f / pk.y : 0.f;
+        // (a sample peak below 1e-20 can only end below the reference's 1e-10 floor: skip the scaling, whose
+        // reciprocal would overflow for denormal peaks)
+        const float sa = pk.x > 1e-20f ? 1.f / pk.x : 0.f, sb = pk.y > 1e-20f ? 1.f / pk.y : 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) { v[j].x *= sa; v[j].y *= sb; }
         fft_forward_local<LOG2M, false>(v, X, Z, st, t, g, active, nop);          // ends with a group barrier
