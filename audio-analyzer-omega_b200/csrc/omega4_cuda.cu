@@ -19,6 +19,7 @@
 #include "blockdft_tc_kernel.cuh"
 #include "fft_core.cuh"
 #include "kweight_kernel.cuh"
+#include "kweight32_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "multires_kernel.cuh"
 #include "stats_kernel.cuh"
@@ -173,6 +174,18 @@ static int launch_kweight_t(const KweightArgs& a, cudaStream_t s) {
 static int launch_kweight(const KweightArgs& a, cudaStream_t s) {
     if (a.x_is_f64) return a.weighted_out ? launch_kweight_t<true, true>(a, s) : launch_kweight_t<true, false>(a, s);
     return a.weighted_out ? launch_kweight_t<false, true>(a, s) : launch_kweight_t<false, false>(a, s);
+}
+
+static int launch_kweight32(const Kweight32Args& a, cudaStream_t s) {
+    const size_t smem = kweight32_smem_bytes();
+    CK(cudaFuncSetAttribute(kweight32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fpc = a.frames_per_warp * KW32_WARPS;
+    const long long grid = (long long)((a.n_frames + fpc - 1) / fpc) * a.n_ch;
+    if (grid <= 0) return OMEGA4_OK;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "kweight grid too large");
+    kweight32_kernel<<<(unsigned)grid, KW32_WARPS * 32, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
 }
 
 static int launch_stats(const StatsArgs& a, cudaStream_t s) {
@@ -394,6 +407,37 @@ static void to_float(const KwBiquad& s, KwBiquadF* d) {
         d->c16[e] = (float)s.c16[e]; d->c17[e] = (float)s.c17[e];
     }
     for (int i = 0; i < KW_SUBMAX; ++i) { d->g[i][0] = (float)s.g[i][0]; d->g[i][1] = (float)s.g[i][1]; }
+}
+
+// float32-state form of one high-pass section (kweight32_kernel.cuh): b = b0 [1, -2, 1] required
+static bool is_highpass_biquad(const KwBiquad& q) {
+    return q.pad == 9 && q.a2 != 0.0 && fabs(q.b1 + 2.0 * q.b0) <= 1e-12 * fabs(q.b0) && fabs(q.b2 - q.b0) <= 1e-12 * fabs(q.b0);
+}
+
+static void build_kw32(const KwBiquad& q, Kw32Sec* o) {
+    const double alpha = 1.0 + q.a1 + q.a2, beta = 1.0 - q.a2;
+    const double bb = -q.b0 * beta, gamma = alpha / bb;
+    o->b0 = (float)q.b0; o->a2 = (float)q.a2; o->gamma = (float)gamma; o->bb = (float)bb;
+    const double M[4] = {1.0 - alpha, bb * q.a2, -gamma, q.a2}; // (z, delta) -> (z + bb delta', delta'),  delta' = a2 delta - gamma z
+    double P[4] = {M[0], M[1], M[2], M[3]};
+    for (int i = 0; i < KW_L; ++i) {                            // P = M^(i+1)
+        if (i < KW_SUBMAX) { o->g[i][0] = (float)P[0]; o->g[i][1] = (float)P[1]; }
+        if (i + 1 == 16) for (int e = 0; e < 4; ++e) o->c16[e] = (float)P[e];
+        if (i + 1 == 17) for (int e = 0; e < 4; ++e) o->c17[e] = (float)P[e];
+        if (i + 1 < KW_L) mat2_mul(M, P, P);
+    }
+    double Q[4] = {P[0], P[1], P[2], P[3]};                     // M^65
+    for (int j = 0; j < 5; ++j) {
+        for (int e = 0; e < 4; ++e) o->phi[j][e] = (float)Q[e];
+        mat2_mul(Q, Q, Q);
+    }
+}
+
+// the batch path's K-weighting runs in the float32-state kernel when the active program is the two
+// high-pass sections blended as f + 0.3 (s - f) (the default); OMEGA4_KW_F64=1 keeps the float64 kernel
+static bool use_kweight32(const omega4_plan* p) {
+    return p->W == KW_W && p->kw_nsec == 2 && p->kw_blend && p->kw_gain == 1.0 && is_highpass_biquad(p->kw[0]) &&
+           is_highpass_biquad(p->kw[1]) && !getenv("OMEGA4_KW_F64");
 }
 
 static void fill_weighting(const omega4_plan* p, KweightArgs* k) {
@@ -811,7 +855,19 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         if (!tp) { int rc = p->scratch_tp.ensure(nser); if (rc) return rc; tp = (double*)p->scratch_tp.p; }
         long long need = (long long)p->W - hist;
         const int first_m = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
-        {
+        if (use_kweight32(p)) {
+            Kweight32Args k;
+            memset(&k, 0, sizeof k);
+            k.x = x; k.ch_stride = ch_stride; k.frame_stride = p->hop;
+            k.frame_off0 = (long long)p->hop - p->W;
+            k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
+            k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
+            k.hann = p->hann32; k.lufs_out = lufs; k.rms_gate = p->kw_gate;
+            build_kw32(p->kw[0], &k.s[0]); build_kw32(p->kw[1], &k.s[1]);
+            Bracket b(p, ms, timing, "kweight_lufs");
+            int rc = launch_kweight32(k, ms);
+            if (rc) return rc;
+        } else {
             KweightArgs k;
             memset(&k, 0, sizeof k);
             k.x = x; k.x_is_f64 = 0; k.ch_stride = ch_stride; k.frame_stride = p->hop;

@@ -337,7 +337,7 @@ def main():
             "metric": METRIC if args.workload == "config2" else METRIC.replace("48 kHz stereo", "96 kHz 8-channel"),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (FFT, combine; 3xTF32 tensor-core GEMM for the few-bin resolutions) + f64 (K-weighting biquads, meter statistics)",
+            "dtype": "f32 (FFT, combine, true peak, K-weighting in a float32 delta-form state; 3xTF32 tensor-core GEMM for the few-bin resolutions) + f64 (meter statistics)",
             "data": "synthetic",
             "config": {"workload": f"{wl_name}: {n_streams} streams x {CHANNELS} ch x {args.seconds} s @{SR // 1000} kHz per GPU, "
                                    f"resolutions {'/'.join(str(c[1]) for c in configs)}, hop 512, 512 target bins (fused output mode B), "
