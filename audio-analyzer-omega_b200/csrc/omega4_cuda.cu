@@ -375,9 +375,12 @@ struct omega4_plan {
         DevBuf in, in16, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
         SideCtx sc;
     };
-    static constexpr int N_SLOTS = 4;
+#ifndef OMEGA4_HOST_SLOTS
+#define OMEGA4_HOST_SLOTS 4
+#endif
+    static constexpr int N_SLOTS = OMEGA4_HOST_SLOTS;
     Slot slots[N_SLOTS];
-    size_t host_chunk_bytes = (size_t)1536 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
+    size_t host_chunk_bytes = (size_t)1024 << 20;  // device bytes per slot (OMEGA4_HOST_CHUNK_MB overrides)
     // OMEGA4_FLAG_CONCURRENT_METERS: the K-weighting + stats kernels run on a side stream, forked /
     // joined with events on the caller's stream
     SideCtx sc;
