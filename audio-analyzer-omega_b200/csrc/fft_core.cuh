@@ -381,5 +381,12 @@ __device__ __forceinline__ void rfft_pair(float2 Zk, float2 Zm, float2 w, float2
 }
 
 __device__ __forceinline__ float cabs(float2 a) { return sqrtf(fmaf(a.x, a.x, a.y * a.y)); }
+// |a| with the hardware square root (one MUFU.SQRT, relative error 2^-23 against 1.2e-3 for the 0.01 dB bar;
+// the IEEE sqrtf above costs ~9 instructions and a divergent slow path per call); squares below 1.2e-38 flush to 0
+__device__ __forceinline__ float cabs_fast(float2 a) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(a.x, a.x, a.y * a.y)));
+    return y;
+}
 
 }  // namespace o4

@@ -73,9 +73,8 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
             const float2 Zm = Z[ZA::at((M - u) & (M - 1))];
             const float2 w = twn[u];
             rfft_pair(Zk, Zm, w, Xk, Xm);
-            mk = cabs(Xk);
-            mm = cabs(Xm);
-            if (bw) { mk *= bw[k]; mm *= bw[km]; }
+            if (all_bins || ink) { mk = cabs_fast(Xk); if (bw) mk *= bw[k]; }
+            if (all_bins || inm) { mm = cabs_fast(Xm); if (bw) mm *= bw[km]; }
         }
         if (mrow) { mrow[k] = mk; mrow[km] = mm; }
         if (crow) { crow[k] = Xk; crow[km] = Xm; }
@@ -98,7 +97,7 @@ __device__ __forceinline__ void multires_combine(const MultiresArgs& a, const fl
             const float m0 = mags[lo - a.need_lo];
             const float m1 = mags[lo + 1 - a.need_lo];
             const float vi = fmaf(m1 - m0, tb.frac[j], m0);
-            val = (vi * a.wnum) / a.wden;
+            val = __fdividef(vi * a.wnum, a.wden);      // (interp * weight) / weight of :389-395, 2 ulp
         }
         orow[tb.idx[j]] = val;
     }
