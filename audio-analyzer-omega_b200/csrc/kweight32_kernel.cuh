@@ -25,7 +25,7 @@
 // RELATIVE precision, so the pole positions keep 7 digits; for content above the cut-off z and d are
 // ~beta |x|, for content below it z ~ -b0 x is smooth and d tiny, so the round-off that the double pole
 // integrates is two orders of magnitude below that of a float32 direct form.  Measured against the float64
-// oracle (tools/proto note in DESIGN.md section 4.3; tests/test_gpu_parity.py): <= 5e-6 LU on windowed
+// oracle (numpy emulation of this exact structure: tests/tools/kweight32_numerics.py, profiles/r01h_kweight32_numerics.txt; on the GPU: tests/test_gpu_parity.py): <= 5e-6 LU on windowed
 // frames of noise, tones 10 Hz .. 10 kHz, DC offsets, clipping, impulses and steps -- the float64 kernel's
 // own level -- against the 0.01 LU bar.
 //

@@ -3,7 +3,7 @@ very different character (digital silence, 1e-7 .. 1e-3 level noise, full-scale 
 offsets, impulses), through the batch entry point, channel by channel against oracle.analyze_channel."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "audio-analyzer-omega_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
