@@ -289,6 +289,7 @@ struct ResInfo {
 // A resolution whose fused output needs only a few FFT bins (blockdft_kernel.cuh)
 struct SparseRes {
     int r = 0, nk = 0, nt = 0, B = 0, col0 = 0;
+    bool td = false;              // time-domain windowed operand: one column pair per (bin, block position), no T
     float2* T = nullptr;          // [nk][B][nt]
     float* kw = nullptr;          // [nk]
     int* tb_pos = nullptr;        // [n_tb]
@@ -472,7 +473,12 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
                             const std::vector<std::vector<int>>& lo, bool tensor, SparseSet* set) {
     const int H = d->hop;
     if ((H % (tensor ? TC_KC : BD_KC)) != 0) return OMEGA4_OK;
-    const int max_cols = tensor ? 512 : 128;              // all TMEM columns / the widest CUDA-core tile
+    // tensor: up to four column tiles of 256 (each tile = all 512 TMEM columns as main | cross); CUDA cores: the widest tile
+    const int max_cols = tensor ? 1024 : 128;
+    // exact (time-domain) windowing for the tensor-core set wherever a frame spans <= 16 hop blocks; longer
+    // transforms (config 5: 32768 / 16384 at hop 512) would need 64 / 32 column pairs per bin and keep the
+    // cosine-sum formulation.  OMEGA4_BLOCKDFT_FD=1 forces the cosine-sum formulation everywhere.
+    const bool allow_td = tensor && !getenv("OMEGA4_BLOCKDFT_FD");
     int order[OMEGA4_MAX_RES];
     for (int r = 0; r < d->n_res; ++r) order[r] = r;
     for (int i = 0; i < d->n_res; ++i)                 // largest transform first
@@ -492,8 +498,39 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         std::sort(bins.begin(), bins.end());
         bins.erase(std::unique(bins.begin(), bins.end()), bins.end());
         if (bins.empty()) continue;
-        // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
         const float* w = d->windows + woff2[r];
+        const double two_pi = 6.283185307179586476925287;
+        const int nk = (int)bins.size();
+        const double fft_cost = 2.5 * N * (ri.log2m + 1);
+        if (allow_td && N / H <= 16 && (double)(2 * nk * (N / H)) * H <= 6.6 * fft_cost && cols + 2 * nk * (N / H) <= max_cols) {
+            // ---- exact windowing: column pair (ki, b) = w[H b + n] e^{-2 pi i k (H b + n) / N}
+            SparseRes& sp = set->sp[set->n];
+            sp.r = r; sp.nk = nk; sp.nt = N / H; sp.B = N / H; sp.col0 = cols; sp.td = true;
+            const int rc_cols = 2 * nk * sp.B;
+            std::vector<float> ec((size_t)H * rc_cols);
+            std::vector<float> kw(nk);
+            for (int ki = 0; ki < nk; ++ki) {
+                kw[ki] = d->bin_weights ? d->bin_weights[boff_of(d, r) + bins[ki]] : 1.f;
+                for (int b = 0; b < sp.B; ++b)
+                    for (int n2 = 0; n2 < H; ++n2) {
+                        const int i = H * b + n2;
+                        const long long ph = ((long long)bins[ki] * i) % N;              // exact phase reduction
+                        const double ang = -two_pi * (double)ph / (double)N;
+                        ec[(size_t)n2 * rc_cols + 2 * (ki * sp.B + b)] = (float)((double)w[i] * cos(ang));
+                        ec[(size_t)n2 * rc_cols + 2 * (ki * sp.B + b) + 1] = (float)((double)w[i] * sin(ang));
+                    }
+            }
+            std::vector<int> pos(idx[r].size(), -1);
+            for (size_t j = 0; j < lo[r].size(); ++j)
+                if (lo[r][j] >= 0) pos[j] = (int)(std::lower_bound(bins.begin(), bins.end(), lo[r][j]) - bins.begin());
+            int rc = upload((void**)&sp.kw, kw.data(), kw.size() * sizeof(float)); if (rc) return rc;
+            rc = upload((void**)&sp.tb_pos, pos.data(), pos.size() * sizeof(int)); if (rc) return rc;
+            set->of_res[r] = set->n++;
+            ecols.push_back(std::move(ec));
+            cols += rc_cols;
+            continue;
+        }
+        // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
         const double phi = 6.283185307179586476925287 / (double)(N - 1);
         double G[3][4] = {{0}};
         for (int i = 0; i < N; ++i) {
@@ -524,12 +561,10 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         tm[nt] = 0; tc[nt] = am[0]; ++nt;
         for (int m = 1; m <= 2; ++m)
             if (fabs(am[m]) > 1e-9) { tm[nt] = m; tc[nt] = 0.5 * am[m]; ++nt; tm[nt] = -m; tc[nt] = 0.5 * am[m]; ++nt; }
-        const int nk = (int)bins.size();
         const int rc_cols = 2 * nk * nt;
         // cost model against the FFT kernel's ~2.5 N log2 N instructions per frame (measured ~22 T instr/s):
         //   CUDA-core GEMM: cols x hop FMAs at ~23 T/s  -> accept below half the FFT's count
         //   tensor-core GEMM: 3 x cols x hop MACs at ~250 T/s (measured, 3xTF32)
-        const double fft_cost = 2.5 * N * (ri.log2m + 1);
         if (!tensor && (double)rc_cols * H * 2.0 > fft_cost) continue;
         if (tensor && (double)rc_cols * H > 6.6 * fft_cost) continue;
         if (cols + rc_cols > max_cols) continue;
@@ -538,7 +573,6 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         std::vector<float> ec((size_t)H * rc_cols);
         std::vector<float2> T((size_t)nk * sp.B * nt);
         std::vector<float> kw(nk);
-        const double two_pi = 6.283185307179586476925287;
         for (int ki = 0; ki < nk; ++ki) {
             kw[ki] = d->bin_weights ? d->bin_weights[boff_of(d, r) + bins[ki]] : 1.f;
             for (int t = 0; t < nt; ++t) {
@@ -999,6 +1033,26 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             if (!use_sparse[r]) continue;
             const ResInfo& ri = p->res[r];
             const SparseRes& sp = set.sp[set.of_res[r]];
+            if (sp.td) {
+                BlockDftSumArgs a;
+                memset(&a, 0, sizeof a);
+                a.Q = Q; a.qs = set.qs; a.col0 = sp.col0; a.nb = nb > 0 ? nb : 0; a.j0 = j0;
+                a.nk = sp.nk; a.B = sp.B; a.kw = sp.kw;
+                a.n_ch = n_ch; a.n_frames = n_hops; a.first_frame = first[r];
+                a.comb_out = combined; a.Tbins = p->T; a.n_tb = ri.n_tb; a.tb_idx = ri.tb_idx; a.tb_pos = sp.tb_pos;
+                a.tb_frac = ri.tb_frac; a.wnum = ri.weight; a.wden = ri.weight;
+                a.fa = blockdft_sum_frames(sp.nk, sp.B);
+                const size_t smem = blockdft_sum_smem_bytes(sp.nk, sp.B, a.fa);
+                CK(cudaFuncSetAttribute(blockdft_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const long long grid = (long long)((n_hops + a.fa - 1) / a.fa) * n_ch;
+                if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft assemble grid too large");
+                char name[32];
+                snprintf(name, sizeof name, "blockdft_asm_%d", ri.n);
+                Bracket b(p, s, timing, name);
+                blockdft_sum_kernel<<<(unsigned)grid, 256, smem, s>>>(a);
+                CK(cudaGetLastError());
+                continue;
+            }
             BlockDftAsmArgs a;
             memset(&a, 0, sizeof a);
             a.Q = Q; a.qs = set.qs; a.col0 = sp.col0; a.nb = nb > 0 ? nb : 0; a.j0 = j0;

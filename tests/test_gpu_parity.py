@@ -7,6 +7,8 @@ measured errors are ~1e-4 dB / 1e-6 LU / 1e-5 dBTP (profiles/parity_r01.txt).
 """
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -257,19 +259,31 @@ def test_blockdft_96k_default_and_window_variants(golden):
         assert ("blockdft_gemm" if fl else "blockdft_tc_gemm") in _kernel_names(p)
         assert_spectrum_close(out["combined"][0, 23], g["combined_h23"], TOL_DB, label="window variants blockdft")
     p.close()
-    # a window that is NOT a cosine sum keeps the FFT path
+    # a window that is NOT a cosine sum: the exact-windowing operand (default) carries any window; the
+    # cosine-sum formulation (OMEGA4_BLOCKDFT_FD=1) keeps the FFT path for it
     rng = np.random.default_rng(5)
     wins = [np.blackman(c[1]).astype(np.float32) for c in BASELINE_CONFIGS]
     wins[0] = (wins[0] * (1 + 0.01 * rng.standard_normal(8192))).astype(np.float32)
-    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512, windows=wins)
-    out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
-    assert not any(n.startswith("blockdft") and "8192" in n for n in _kernel_names(p)) and "multires_fft_8192" in _kernel_names(p)
     mr = O.OracleMultiResFFT(48000, 20000, list(O.BASELINE_CONFIGS))
     mr.windows[0] = wins[0]
     for k in range(24):
         res = mr.process_audio_chunk(x[k * HOP:(k + 1) * HOP])
-    assert_spectrum_close(out["combined"][0, 23], mr.combine(res, 512)[0], TOL_DB, label="custom window")
-    p.close()
+    want = mr.combine(res, 512)[0]
+    for fd in (False, True):
+        if fd:
+            os.environ["OMEGA4_BLOCKDFT_FD"] = "1"
+        try:
+            p = AnalysisPlan(48000, BASELINE_CONFIGS, 512, windows=wins)
+            out = p.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS)
+            names = _kernel_names(p)
+            if fd:
+                assert "multires_fft_8192" in names and "blockdft_asm_8192" not in names and "blockdft_asm_4096" in names
+            else:
+                assert "blockdft_asm_8192" in names and "multires_fft_8192" not in names
+            assert_spectrum_close(out["combined"][0, 23], want, TOL_DB, label="custom window")
+            p.close()
+        finally:
+            os.environ.pop("OMEGA4_BLOCKDFT_FD", None)
 
 
 # ------------------------------------------------------------------ section 8f rank 1: app post-processing

@@ -43,18 +43,19 @@ def spectrum_gate(got, ref, mags, label, mode, tol_db=0.01, rel_floor_db=-60.0):
     window has already left), the same absolute error below that; and the coverage pattern: where the
     reference is exactly zero because no resolution contributes, so is the product.
 
-    The hop-block DFT modes ("tc", "fp32") apply the window in the frequency domain, so their rounding error
-    scales with the UNWINDOWED energy inside the frame: a burst sitting under the window's near-zero edge
-    leaves an error of 1e-7 of its own magnitude on a value the window has attenuated by 60 dB or more.  For
-    them the 60 dB are therefore counted from the largest magnitude the transform shows while the same
-    samples are inside its window (+- N/hop hops); the full-FFT mode ("fft", OMEGA4_FLAG_NO_BLOCKDFT) is
-    held to the per-frame statement."""
+    The default tensor-core hop-block DFT ("tc": the window is part of the GEMM operand) and the full-FFT mode
+    ("fft", OMEGA4_FLAG_NO_BLOCKDFT) are held to this per-frame statement.  The cosine-sum hop-block modes
+    ("tcfd" = OMEGA4_BLOCKDFT_FD=1, and "fp32" = OMEGA4_FLAG_NO_TENSOR) apply the window in the frequency
+    domain, so their rounding error scales with the UNWINDOWED energy inside the frame: a burst sitting under
+    the window's near-zero edge leaves an error of 1e-7 of its own magnitude on a value the window has
+    attenuated by 60 dB or more.  For them the 60 dB are counted from the largest magnitude the transform
+    shows while the same samples are inside its window (+- N/hop hops)."""
     tf = np.linspace(0.0, 20000.0, ref.shape[1])
     floor = np.zeros(ref.shape)
     for i, ((lo, hi), n, _h, _w, _t) in enumerate(BASELINE_CONFIGS):
         first, m = mags[i]
         peak = np.zeros(ref.shape[0]); peak[first:first + len(m)] = m.max(axis=1)
-        if mode != "fft" and n > 2048:                     # resolutions served by the hop-block DFT
+        if mode in ("fp32", "tcfd") and n > 2048:                     # resolutions served by the hop-block DFT
             B = n // HOP
             pad = np.pad(peak, B)
             peak = np.max(np.stack([pad[d:d + len(peak)] for d in range(2 * B + 1)]), axis=0)
@@ -70,8 +71,10 @@ def spectrum_gate(got, ref, mags, label, mode, tol_db=0.01, rel_floor_db=-60.0):
     return float(np.abs(db(g[sig], 1e-30) - db(r[sig], 1e-30)).max()) if sig.any() else 0.0
 
 
+if mode == "tcfd":
+    os.environ["OMEGA4_BLOCKDFT_FD"] = "1"
 plan = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
-got = plan.analyze_host(x, want_series=True, flags={"tc": 0, "fp32": N.FLAG_NO_TENSOR, "fft": N.FLAG_NO_BLOCKDFT}[mode])
+got = plan.analyze_host(x, want_series=True, flags={"tc": 0, "tcfd": 0, "fp32": N.FLAG_NO_TENSOR, "fft": N.FLAG_NO_BLOCKDFT}[mode])
 worst = {"spec_db": 0.0, "lufs": 0.0, "tp": 0.0, "meters": 0.0}
 for c in range(n_ch):
     ref = O.analyze_channel(x[c], 48000, O.BASELINE_CONFIGS, keep_magnitudes=True)
