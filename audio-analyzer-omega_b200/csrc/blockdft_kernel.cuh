@@ -384,4 +384,54 @@ inline int blockdft_sum_frames(int nk, int B) {
     return fa;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Finish of the fused path (blockdft_tc_kernel with X output): |X| * weight and the np.interp segments from
+// the complex bins X[ch][bin][frame] the GEMM epilogue assembled.  64 frames per CTA, lanes over frames.
+// ---------------------------------------------------------------------------------------------
+struct BlockDftFinishArgs {
+    const float2* X;           // [n_ch][nkx][n_frames]
+    int nkx, xoff, nk;
+    const float* kw;           // [nk]
+    int n_ch, n_frames, first_frame;
+    float* comb_out;
+    int Tbins, n_tb;
+    const int* tb_idx;
+    const int* tb_pos;
+    const float* tb_frac;
+    float wnum, wden;
+};
+constexpr int BD_FIN_FRAMES = 64;
+
+__global__ void __launch_bounds__(256)
+blockdft_finish_kernel(const __grid_constant__ BlockDftFinishArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* mags = reinterpret_cast<float*>(smem_raw);     // [nk][FRAMES + 1]
+    constexpr int MS = BD_FIN_FRAMES + 1;
+    const int tiles_per_ch = (a.n_frames + BD_FIN_FRAMES - 1) / BD_FIN_FRAMES;
+    const int ch = blockIdx.x / tiles_per_ch;
+    const int f0 = (blockIdx.x % tiles_per_ch) * BD_FIN_FRAMES;
+    const int nf = min(BD_FIN_FRAMES, a.n_frames - f0);
+    const int tid = threadIdx.x;
+    const float2* xch = a.X + ((size_t)ch * a.nkx + a.xoff) * a.n_frames + f0;
+    for (int it = tid; it < BD_FIN_FRAMES * a.nk; it += 256) {
+        const int fl = it % BD_FIN_FRAMES, ki = it / BD_FIN_FRAMES;
+        if (fl < nf) mags[ki * MS + fl] = cabs_fast(__ldg(xch + (size_t)ki * a.n_frames + fl)) * a.kw[ki];
+    }
+    __syncthreads();
+    for (int it = tid; it < nf * a.n_tb; it += 256) {
+        const int fl = it / a.n_tb, j = it % a.n_tb;
+        const int f = f0 + fl;
+        const int pos = a.tb_pos[j];
+        float val = 0.f;
+        if (pos >= 0 && f >= a.first_frame) {
+            const float m0 = mags[pos * MS + fl], m1 = mags[(pos + 1) * MS + fl];
+            const float vi = fmaf(m1 - m0, a.tb_frac[j], m0);
+            val = __fdividef(vi * a.wnum, a.wden);
+        }
+        a.comb_out[((size_t)ch * a.n_frames + f) * a.Tbins + a.tb_idx[j]] = val;
+    }
+}
+
+inline size_t blockdft_finish_smem_bytes(int nk) { return (size_t)nk * (BD_FIN_FRAMES + 1) * sizeof(float) + 16; }
+
 }  // namespace o4

@@ -50,7 +50,18 @@ struct BlockDftTcArgs {
     const uint8_t* Eimg;       // [n_halves][hop/KC][2 (hi, lo)][TC_B_BYTES] pre-swizzled operand images
     float* Q;                  // [n_ch][nb][qs]
     int qs;                    // TC_BN * n_halves
+    // Fused frame assembly (exact-windowing operand only, see blockdft_kernel.cuh): instead of writing Q, the
+    // epilogue adds the block rows of every frame, X_f[k] = sum_b Q_{f+1-B+b}[k][b], through shared memory
+    // and writes the complex bins X[ch][bin][frame]; Q never leaves the SM.  Frames that straddle two row
+    // tiles are completed with atomicAdd on the zero-initialised X (B - 1 of 128 frames per tile and side).
+    float2* X;                 // nullptr: plain Q output
+    int n_frames;              // frames (= hops) per channel; frame f ends with hop block f
+    int nkx;                   // bins per frame over all fused resolutions
+    short gB[32];              // per 32-column group (n_halves * 8): block positions per bin (2, 4, 8, 16; 0 = unused group)
+    short gX[32];              // per group: index of its first bin in [0, nkx)
+    short gN[32];              // per group: bins present (<= 16 / B)
 };
+constexpr int TC_XROW = 17;          // float2 row stride of the epilogue exchange strip (conflict free)
 
 // byte offset of (row, 16-byte chunk c in 0..3) inside a K-major SWIZZLE_64B tile of 64-byte rows
 __host__ __device__ __forceinline__ int tc_sw64_offset(int row, int c) {
@@ -258,22 +269,70 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
         const int c0 = (TC_MH == 2) ? 0 : grp * (TC_BN / 2);
         constexpr int NCG = (TC_MH == 2) ? TC_BN / 32 : TC_BN / 64;
         const int row = row0 + mh * 128 + quad * 32 + lane;
-        float* qrow = a.Q + ((size_t)ch * a.nb + (row < a.nb ? row : 0)) * a.qs + half * TC_BN + c0;
+        if (TC_MH == 1 && a.X) {
+            // ---- fused frame assembly.  The 128 threads of a group own the 128 rows of the tile for their
+            // 128 columns; the operand stages are idle now and serve as the exchange strip.
+            float2* S = reinterpret_cast<float2*>(tiles) + grp * (128 * TC_XROW);
+            const int r = quad * 32 + lane;                           // local row = local index of the frame's last block
 #pragma unroll 1
-        for (int cg = 0; cg < NCG; ++cg) {
-            uint32_t v[32], c[32];
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mh * TC_BN + c0 + cg * 32);
-            tc_tmem_ld32(taddr, v);
-            tc_tmem_ld32(taddr + 256, c);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < a.nb) {
-                float4* dst = reinterpret_cast<float4*>(qrow + cg * 32);
+            for (int cg = 0; cg < NCG; ++cg) {
+                uint32_t v[32], c[32];
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c0 + cg * 32);
+                tc_tmem_ld32(taddr, v);
+                tc_tmem_ld32(taddr + 256, c);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int gi = half * (TC_BN / 32) + (c0 >> 5) + cg;
+                const int B = a.gB[gi], nbin = a.gN[gi], xb0 = a.gX[gi];
+                if (B > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    dst[i] = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(c[4 * i]),
-                                         __uint_as_float(v[4 * i + 1]) + __uint_as_float(c[4 * i + 1]),
-                                         __uint_as_float(v[4 * i + 2]) + __uint_as_float(c[4 * i + 2]),
-                                         __uint_as_float(v[4 * i + 3]) + __uint_as_float(c[4 * i + 3]));
+                    for (int i = 0; i < 16; ++i)
+                        S[r * TC_XROW + i] = make_float2(__uint_as_float(v[2 * i]) + __uint_as_float(c[2 * i]),
+                                                         __uint_as_float(v[2 * i + 1]) + __uint_as_float(c[2 * i + 1]));
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+                if (B > 0) {
+                    // task 0: the frame ending at local row r; task 1 (r < B - 1): the frame ending r + 1 rows past the tile
+#pragma unroll 1
+                    for (int task = 0; task < 2; ++task) {
+                        if (task == 1 && r >= B - 1) break;
+                        const int R = task == 0 ? r : 128 + r;
+                        const int lo = max(0, R - B + 1), hi = min(127, R);
+                        const long long f = (long long)a.j0 + row0 + R;   // frame index = index of its last hop block
+                        if (f < 0 || f >= a.n_frames) continue;
+                        const bool whole = (R - B + 1 >= 0) && (R <= 127);
+                        for (int q = 0; q < nbin; ++q) {
+                            float2 acc = make_float2(0.f, 0.f);
+                            const float2* sp = S + q * B - (R - B + 1);      // element (rho, b = rho - (R - B + 1)) of bin q
+                            for (int rho = lo; rho <= hi; ++rho) {
+                                const float2 u = sp[rho * TC_XROW + rho];
+                                acc.x += u.x; acc.y += u.y;
+                            }
+                            float2* dst = a.X + ((size_t)ch * a.nkx + xb0 + q) * a.n_frames + f;
+                            if (whole) *dst = acc;
+                            else { atomicAdd(&dst->x, acc.x); atomicAdd(&dst->y, acc.y); }
+                        }
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            }
+        } else {
+            float* qrow = a.Q + ((size_t)ch * a.nb + (row < a.nb ? row : 0)) * a.qs + half * TC_BN + c0;
+#pragma unroll 1
+            for (int cg = 0; cg < NCG; ++cg) {
+                uint32_t v[32], c[32];
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mh * TC_BN + c0 + cg * 32);
+                tc_tmem_ld32(taddr, v);
+                tc_tmem_ld32(taddr + 256, c);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < a.nb) {
+                    float4* dst = reinterpret_cast<float4*>(qrow + cg * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(c[4 * i]),
+                                             __uint_as_float(v[4 * i + 1]) + __uint_as_float(c[4 * i + 1]),
+                                             __uint_as_float(v[4 * i + 2]) + __uint_as_float(c[4 * i + 2]),
+                                             __uint_as_float(v[4 * i + 3]) + __uint_as_float(c[4 * i + 3]));
+                }
             }
         }
     }

@@ -290,6 +290,7 @@ struct ResInfo {
 struct SparseRes {
     int r = 0, nk = 0, nt = 0, B = 0, col0 = 0;
     bool td = false;              // time-domain windowed operand: one column pair per (bin, block position), no T
+    int xoff = 0;                 // first bin of this resolution in the fused X rows
     float2* T = nullptr;          // [nk][B][nt]
     float* kw = nullptr;          // [nk]
     int* tb_pos = nullptr;        // [n_tb]
@@ -304,6 +305,11 @@ struct SparseSet {
     float* E = nullptr;           // CUDA-core GEMM operand [hop][qs]            (blockdft_kernel.cuh)
     uint8_t* Eimg = nullptr;      // tensor-core operand images, hi/lo, swizzled  (blockdft_tc_kernel.cuh)
     int n_halves = 0;
+    // fused frame assembly in the GEMM epilogue: possible when every resolution of the set uses the exact-
+    // windowing operand with 2 / 4 / 8 / 16 block positions per bin and 32-column aligned blocks
+    bool fusable = false;
+    int nkx = 0;                  // bins per frame over all resolutions of the set
+    short gB[32], gX[32], gN[32]; // per 32-column group of the GEMM: positions per bin, first bin, bins present
     SparseSet() { for (int i = 0; i < OMEGA4_MAX_RES; ++i) of_res[i] = -1; }
     void release() {
         for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(sp[i].T); cudaFree(sp[i].kw); cudaFree(sp[i].tb_pos); }
@@ -502,8 +508,10 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         const double two_pi = 6.283185307179586476925287;
         const int nk = (int)bins.size();
         const double fft_cost = 2.5 * N * (ri.log2m + 1);
-        if (allow_td && N / H <= 16 && (double)(2 * nk * (N / H)) * H <= 6.6 * fft_cost && cols + 2 * nk * (N / H) <= max_cols) {
+        if (allow_td && N / H <= 16 && (double)(2 * nk * (N / H)) * H <= 6.6 * fft_cost &&
+            ((cols + 31) & ~31) + 2 * nk * (N / H) <= max_cols) {
             // ---- exact windowing: column pair (ki, b) = w[H b + n] e^{-2 pi i k (H b + n) / N}
+            cols = (cols + 31) & ~31;                      // whole 32-column groups per resolution (fused epilogue)
             SparseRes& sp = set->sp[set->n];
             sp.r = r; sp.nk = nk; sp.nt = N / H; sp.B = N / H; sp.col0 = cols; sp.td = true;
             const int rc_cols = 2 * nk * sp.B;
@@ -528,6 +536,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
             set->of_res[r] = set->n++;
             ecols.push_back(std::move(ec));
             cols += rc_cols;
+            cols = (cols + 31) & ~31;
             continue;
         }
         // least-squares fit  w[i] = a0 + a1 cos(phi i) + a2 cos(2 phi i),  phi = 2 pi / (N - 1)
@@ -615,6 +624,28 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
     // the K-major SWIZZLE_64B shared-memory layout
     set->n_halves = (cols + TC_BN - 1) / TC_BN;
     set->qs = set->n_halves * TC_BN;
+    {
+        bool ok = set->n_halves * (TC_BN / 32) <= 32;
+        int xo = 0;
+        for (int si = 0; si < set->n; ++si) {
+            SparseRes& sp = set->sp[si];
+            ok = ok && sp.td && (sp.B == 2 || sp.B == 4 || sp.B == 8 || sp.B == 16) && (sp.col0 % 32) == 0;
+            sp.xoff = xo; xo += sp.nk;
+        }
+        set->nkx = xo;
+        for (int g = 0; g < 32; ++g) { set->gB[g] = 0; set->gX[g] = 0; set->gN[g] = 0; }
+        if (ok)
+            for (int si = 0; si < set->n; ++si) {
+                const SparseRes& sp = set->sp[si];
+                const int per = 16 / sp.B;                 // bins per 32-column group
+                for (int k0 = 0; k0 < sp.nk; k0 += per) {
+                    const int g = (sp.col0 + 2 * k0 * sp.B) / 32;
+                    set->gB[g] = (short)sp.B; set->gX[g] = (short)(sp.xoff + k0);
+                    set->gN[g] = (short)((sp.nk - k0 < per) ? sp.nk - k0 : per);
+                }
+            }
+        set->fusable = ok && !getenv("OMEGA4_BLOCKDFT_UNFUSED");
+    }
     const int nkc = H / TC_KC;
     std::vector<uint8_t> img((size_t)set->n_halves * nkc * 2 * TC_B_BYTES, 0);
     for (int si = 0; si < set->n; ++si) {
@@ -1003,8 +1034,11 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             if (use_sparse[r]) { const int j = first[r] + 1 - set.sp[set.of_res[r]].B; if (j < j0) j0 = j; }
         const int nb = n_hops - j0;
         const float* Q = nullptr;
+        const bool fusedx = tensor && set.fusable;        // frames assembled in the GEMM epilogue, no Q
         if (nb > 0) {
-            int rc = qbuf->ensure((size_t)n_ch * nb * set.qs * sizeof(float));
+            const size_t qbytes = fusedx ? (size_t)n_ch * set.nkx * n_hops * sizeof(float2)
+                                         : (size_t)n_ch * nb * set.qs * sizeof(float);
+            int rc = qbuf->ensure(qbytes);
             if (rc) return rc;
             Q = (float*)qbuf->p;
             if (tensor) {
@@ -1012,6 +1046,11 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 memset(&g, 0, sizeof g);
                 g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
                 g.n_halves = set.n_halves; g.Eimg = set.Eimg; g.Q = (float*)qbuf->p; g.qs = set.qs;
+                if (fusedx) {
+                    g.X = (float2*)qbuf->p; g.n_frames = n_hops; g.nkx = set.nkx;
+                    memcpy(g.gB, set.gB, sizeof g.gB); memcpy(g.gX, set.gX, sizeof g.gX); memcpy(g.gN, set.gN, sizeof g.gN);
+                    CK(cudaMemsetAsync(qbuf->p, 0, qbytes, s));      // frames that straddle row tiles are completed with atomics
+                }
                 const size_t smem = blockdft_tc_smem_bytes();
                 CK(cudaFuncSetAttribute(blockdft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const long long grid = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
@@ -1033,6 +1072,24 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             if (!use_sparse[r]) continue;
             const ResInfo& ri = p->res[r];
             const SparseRes& sp = set.sp[set.of_res[r]];
+            if (sp.td && fusedx) {
+                BlockDftFinishArgs a;
+                memset(&a, 0, sizeof a);
+                a.X = (const float2*)Q; a.nkx = set.nkx; a.xoff = sp.xoff; a.nk = sp.nk; a.kw = sp.kw;
+                a.n_ch = n_ch; a.n_frames = n_hops; a.first_frame = first[r];
+                a.comb_out = combined; a.Tbins = p->T; a.n_tb = ri.n_tb; a.tb_idx = ri.tb_idx; a.tb_pos = sp.tb_pos;
+                a.tb_frac = ri.tb_frac; a.wnum = ri.weight; a.wden = ri.weight;
+                const size_t smem = blockdft_finish_smem_bytes(sp.nk);
+                CK(cudaFuncSetAttribute(blockdft_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const long long grid = (long long)((n_hops + BD_FIN_FRAMES - 1) / BD_FIN_FRAMES) * n_ch;
+                if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft finish grid too large");
+                char name[32];
+                snprintf(name, sizeof name, "blockdft_asm_%d", ri.n);
+                Bracket b(p, s, timing, name);
+                blockdft_finish_kernel<<<(unsigned)grid, 256, smem, s>>>(a);
+                CK(cudaGetLastError());
+                continue;
+            }
             if (sp.td) {
                 BlockDftSumArgs a;
                 memset(&a, 0, sizeof a);
@@ -1132,8 +1189,11 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
     size_t per_ch = (size_t)dstride * sizeof(float) + (size_t)n_hops * 2 * sizeof(double) + ST_STATE * sizeof(double);
     if (combined) per_ch += (size_t)n_hops * p->T * sizeof(float);
     {
-        const int qs = p->set_tc.qs > p->set_cc.qs ? p->set_tc.qs : p->set_cc.qs;
-        if (combined && qs > 0) per_ch += (size_t)(n_hops + 64) * qs * sizeof(float);
+        const bool tensor_sel = p->set_tc.n > 0 && (p->tensor_default ? !(flags & OMEGA4_FLAG_NO_TENSOR) : (flags & OMEGA4_FLAG_TENSOR) != 0);
+        const SparseSet& sset = tensor_sel ? p->set_tc : p->set_cc;
+        if (combined && sset.n > 0 && !(flags & OMEGA4_FLAG_NO_BLOCKDFT))
+            per_ch += (tensor_sel && sset.fusable) ? (size_t)(n_hops + 64) * sset.nkx * sizeof(float2)
+                                                   : (size_t)(n_hops + 64) * sset.qs * sizeof(float);
     }
     if (meters) per_ch += (size_t)n_hops * 5 * sizeof(float);
     bool want_mag[OMEGA4_MAX_RES] = {false};
