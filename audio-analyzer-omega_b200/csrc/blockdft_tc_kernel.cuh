@@ -35,6 +35,12 @@ constexpr int TC_BM = 128 * TC_MH;  // hop blocks per CTA
 constexpr int TC_BN = 256 / TC_MH;  // columns per CTA (UMMA N)
 constexpr int TC_KC = 16;           // samples per K chunk: 64-byte rows
 constexpr int TC_STAGES = 4;
+#ifndef TC_EXPERIMENT_KS
+#define TC_EXPERIMENT_KS 2          // timing experiments only: 1 issues half of the MMAs (wrong results)
+#endif
+#ifndef TC_PG
+#define TC_PG 4                     // producer groups = chunks produced side by side (divides 8 warps)
+#endif
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;     // 8 / 16 KB per (hi | lo)
 constexpr int TC_B_BYTES = TC_BN * TC_KC * 4;     // 16 / 8 KB per (hi | lo)
@@ -133,12 +139,47 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
-// Warp roles: warps 0..7 (256 threads) produce the A tiles and later run the epilogue; warp 8, lane 0
-// requests the B images (bulk TMA) and issues every tcgen05.mma.  Three mbarrier rings tie them together:
-//   bar_a[s]  256 arrivals  A_hi / A_lo of the stage are written and fenced for the async proxy
+
+// Fused frame assembly of one 32-column group: S holds the 128 rows x 16 complex columns (bin q, block position
+// b at column q B + b).  Task 0: the frame whose last hop block is local row r; task 1 (r < B - 1): the frame that
+// ends r + 1 rows past the tile.  Frames that lie wholly inside the tile are stored, the others added atomically.
+template <int B>
+__device__ __forceinline__ void tc_frame_sums(const BlockDftTcArgs& a, const float2* S, int r, int row0, int ch, int nbin, int xb0) {
+    constexpr int PER = 16 / B;
+#pragma unroll
+    for (int task = 0; task < 2; ++task) {
+        if (task == 1 && r >= B - 1) break;
+        const int R = task == 0 ? r : 128 + r;
+        const long long f = (long long)a.j0 + row0 + R;   // frame index = index of its last hop block
+        if (f < 0 || f >= a.n_frames) continue;
+        const bool whole = (R - B + 1 >= 0) && (R <= 127);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            if (q >= nbin) break;
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int rho = R - B + 1 + b;
+                float2 u = make_float2(0.f, 0.f);
+                if (rho >= 0 && rho <= 127) u = S[rho * TC_XROW + q * B + b];
+                if (b & 1) { acc1.x += u.x; acc1.y += u.y; } else { acc0.x += u.x; acc0.y += u.y; }
+            }
+            const float2 acc = make_float2(acc0.x + acc1.x, acc0.y + acc1.y);
+            float2* dst = a.X + ((size_t)ch * a.nkx + xb0 + q) * a.n_frames + f;
+            if (whole) *dst = acc;
+            else { atomicAdd(&dst->x, acc.x); atomicAdd(&dst->y, acc.y); }
+        }
+    }
+}
+
+// Warp roles: warps 0..7 (256 threads) produce the A tiles and later run the epilogue; warp 8, lane 0 issues
+// every tcgen05.mma and waits for operands only; warp 9, lane 0 requests the B images (bulk TMA) as stages
+// retire (one thread doing both had to wait for chunk k-2 to COMPLETE before issuing chunk k, which left
+// the tensor pipe one chunk of work to hide the completion round trip).  Three mbarrier rings tie them together:
+//   bar_a[s]  8 / TC_PG arrivals (one per warp of the producer group) A_hi / A_lo of the stage are written and fenced
 //   bar_b[s]  tx bytes      the B image of the stage has landed
 //   bar_m[s]  tcgen05.commit: every MMA issued so far (in particular those reading stage s) has retired
-__global__ void __launch_bounds__(TC_THREADS + 32, 1)
+__global__ void __launch_bounds__(TC_THREADS + 64, 1)
 blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     extern __shared__ __align__(16) uint8_t tc_smem_raw[];
     // swizzled operand tiles need a 1024-byte aligned base (the swizzle is a function of address bits)
@@ -146,7 +187,8 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     uint64_t* bar_a = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* bar_b = bar_a + TC_STAGES;
     uint64_t* bar_m = bar_b + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_m + TC_STAGES);
+    uint64_t* bar_done = bar_m + TC_STAGES;       // one commit after the last MMA: the epilogue's start signal
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_per_ch = (a.nb + TC_BM - 1) / TC_BM;
@@ -160,8 +202,9 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            tc_mbar_init(bar_a + s, TC_THREADS); tc_mbar_init(bar_b + s, 1); tc_mbar_init(bar_m + s, 1);
+            tc_mbar_init(bar_a + s, TC_THREADS / 32 / TC_PG); tc_mbar_init(bar_b + s, 1); tc_mbar_init(bar_m + s, 1);
         }
+        tc_mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -174,25 +217,28 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == TC_THREADS / 32) {
-        // ===== MMA + B-operand issuer (one thread) =====
+    if (warp == TC_THREADS / 32 + 1) {
+        // ===== B-operand issuer (one thread): runs up to STAGES chunks ahead of the MMAs' completion =====
         if (lane == 0) {
-            constexpr int AHEAD = TC_STAGES - 2;                          // B chunks requested ahead of use
-            for (int kc = 0; kc < AHEAD && kc < n_kc; ++kc) {
-                tc_mbar_expect_tx(bar_b + kc, 2 * TC_B_BYTES);
-                tc_bulk_g2s(tiles + kc * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kc * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + kc);
+            for (int kb = 0; kb < n_kc; ++kb) {
+                const int sb = kb % TC_STAGES;
+                // the stage was last read by chunk kb - STAGES
+                if (kb >= TC_STAGES) tc_mbar_wait(bar_m + sb, (uint32_t)(kb / TC_STAGES - 1) & 1);
+#ifdef TC_EXPERIMENT_B_DIV      /* timing experiment only (wrong results): fetch 1/DIV of the B bytes */
+                tc_mbar_expect_tx(bar_b + sb, 2 * TC_B_BYTES / TC_EXPERIMENT_B_DIV);
+                tc_bulk_g2s(tiles + sb * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kb * 2 * TC_B_BYTES, 2 * TC_B_BYTES / TC_EXPERIMENT_B_DIV, bar_b + sb);
+#else
+                tc_mbar_expect_tx(bar_b + sb, 2 * TC_B_BYTES);
+                tc_bulk_g2s(tiles + sb * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kb * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + sb);
+#endif
             }
+        }
+    } else if (warp == TC_THREADS / 32) {
+        // ===== MMA issuer (one thread): never waits for a completion, only for operands =====
+        if (lane == 0) {
             for (int kc = 0; kc < n_kc; ++kc) {
                 const int s = kc % TC_STAGES;
                 const uint32_t use = (uint32_t)(kc / TC_STAGES);
-                // request B of chunk kc + AHEAD: its stage was last read by chunk kc + AHEAD - STAGES = kc - 2
-                const int kb = kc + AHEAD;
-                if (kb < n_kc) {
-                    if (kc >= 2) tc_mbar_wait(bar_m + (kc - 2) % TC_STAGES, (uint32_t)((kc - 2) / TC_STAGES) & 1);
-                    const int sb = kb % TC_STAGES;
-                    tc_mbar_expect_tx(bar_b + sb, 2 * TC_B_BYTES);
-                    tc_bulk_g2s(tiles + sb * TC_STAGE_BYTES + 2 * TC_A_BYTES, eimg + (size_t)kb * 2 * TC_B_BYTES, 2 * TC_B_BYTES, bar_b + sb);
-                }
                 tc_mbar_wait(bar_a + s, use & 1);
                 tc_mbar_wait(bar_b + s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -200,7 +246,7 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
 #pragma unroll
                 for (int mh = 0; mh < TC_MH; ++mh) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
+                    for (int ks = 0; ks < TC_EXPERIMENT_KS; ++ks) {
                         const uint64_t d_ahi = tc_desc_sw64(sa + mh * (TC_A_BYTES / TC_MH) + ks * 32);
                         const uint64_t d_alo = tc_desc_sw64(sa + TC_A_BYTES + mh * (TC_A_BYTES / TC_MH) + ks * 32);
                         const uint64_t d_bhi = tc_desc_sw64(sa + 2 * TC_A_BYTES + ks * 32);
@@ -213,15 +259,21 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
                 }
                 tc_commit(bar_m + s);
             }
+            tc_commit(bar_done);
         }
     } else {
-        // ===== A producers: 4 TC_BM 16-byte pieces per chunk, piece p = tid + 256 q -> row p/4, chunk p%4 =====
-        constexpr int NQ = TC_BM * 4 / TC_THREADS;
+        // ===== A producers.  TC_PG groups of 256 / TC_PG threads each own every TC_PG-th chunk: a chunk costs its
+        // producer a wait + STS + fence.proxy.async + arrive round trip of ~1000 cycles that no amount of
+        // look-ahead shortens (measured: halving the MMAs or the B bytes changed nothing, the chain did), so
+        // TC_PG chunks are kept in flight side by side instead of one after the other =====
+        constexpr int PGT = TC_THREADS / TC_PG;                  // threads per producer group
+        constexpr int NQ = TC_BM * 4 / PGT;                      // 16-byte pieces per thread and chunk
+        const int pg = tid / PGT, tg = tid % PGT;
         const float4* a_src[NQ];
         int a_off[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const int p = tid + TC_THREADS * q;
+            const int p = tg + PGT * q;
             const int row = p >> 2, c = p & 3;
             int r = row0 + row;
             if (r >= a.nb) r = a.nb - 1;                      // rows past the end: computed, never stored
@@ -230,17 +282,19 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
         }
         float4 nxt[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) nxt[q] = __ldg(a_src[q]);
-        for (int kc = 0; kc < n_kc; ++kc) {
+        for (int q = 0; q < NQ; ++q) nxt[q] = (pg < n_kc) ? __ldg(a_src[q] + pg * (TC_KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kc = pg; kc < n_kc; kc += TC_PG) {
             const int s = kc % TC_STAGES;
             uint8_t* st = tiles + s * TC_STAGE_BYTES;
             float4 cur[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) cur[q] = nxt[q];
-            if (kc + 1 < n_kc) {
+#ifndef TC_EXPERIMENT_NO_LDG
+            if (kc + TC_PG < n_kc) {
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) nxt[q] = __ldg(a_src[q] + (kc + 1) * (TC_KC / 4));
+                for (int q = 0; q < NQ; ++q) nxt[q] = __ldg(a_src[q] + (kc + TC_PG) * (TC_KC / 4));
             }
+#endif
             // the MMAs that read this stage (chunk kc - STAGES) must have retired before it is overwritten
             if (kc >= TC_STAGES) tc_mbar_wait(bar_m + s, (uint32_t)(kc / TC_STAGES - 1) & 1);
 #pragma unroll
@@ -254,14 +308,13 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
                 *reinterpret_cast<float4*>(st + TC_A_BYTES + a_off[q]) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
-            tc_mbar_arrive(bar_a + s);
+            __syncwarp();                                                      // one arrival per warp
+            if (lane == 0) tc_mbar_arrive(bar_a + s);
         }
-        // all MMAs retired <=> the last commit has arrived (a commit tracks every prior tcgen05.mma)
-        {
-            const int last = n_kc - 1;
-            tc_mbar_wait(bar_m + (last % TC_STAGES), (uint32_t)(last / TC_STAGES) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
+        // all MMAs retired <=> the final commit has arrived.  (Not bar_m of the last stage: a producer group that
+        // never waited on that stage inside the loop could see an older phase of the same parity as complete.)
+        tc_mbar_wait(bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31; the two warp groups split the row halves
         // (TC_MH = 2) or the columns (TC_MH = 1); main + cross accumulators are added in registers
         const int grp = warp >> 2, quad = warp & 3;
@@ -283,35 +336,26 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int gi = half * (TC_BN / 32) + (c0 >> 5) + cg;
                 const int B = a.gB[gi], nbin = a.gN[gi], xb0 = a.gX[gi];
+#ifdef TC_EXPERIMENT_NO_EPI
+                if (B > 1000) {
+#else
                 if (B > 0) {
+#endif
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         S[r * TC_XROW + i] = make_float2(__uint_as_float(v[2 * i]) + __uint_as_float(c[2 * i]),
                                                          __uint_as_float(v[2 * i + 1]) + __uint_as_float(c[2 * i + 1]));
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+#ifdef TC_EXPERIMENT_NO_EPI
+                if (B > 1000) {
+#else
                 if (B > 0) {
-                    // task 0: the frame ending at local row r; task 1 (r < B - 1): the frame ending r + 1 rows past the tile
-#pragma unroll 1
-                    for (int task = 0; task < 2; ++task) {
-                        if (task == 1 && r >= B - 1) break;
-                        const int R = task == 0 ? r : 128 + r;
-                        const int lo = max(0, R - B + 1), hi = min(127, R);
-                        const long long f = (long long)a.j0 + row0 + R;   // frame index = index of its last hop block
-                        if (f < 0 || f >= a.n_frames) continue;
-                        const bool whole = (R - B + 1 >= 0) && (R <= 127);
-                        for (int q = 0; q < nbin; ++q) {
-                            float2 acc = make_float2(0.f, 0.f);
-                            const float2* sp = S + q * B - (R - B + 1);      // element (rho, b = rho - (R - B + 1)) of bin q
-                            for (int rho = lo; rho <= hi; ++rho) {
-                                const float2 u = sp[rho * TC_XROW + rho];
-                                acc.x += u.x; acc.y += u.y;
-                            }
-                            float2* dst = a.X + ((size_t)ch * a.nkx + xb0 + q) * a.n_frames + f;
-                            if (whole) *dst = acc;
-                            else { atomicAdd(&dst->x, acc.x); atomicAdd(&dst->y, acc.y); }
-                        }
-                    }
+#endif
+                    if (B == 16) tc_frame_sums<16>(a, S, r, row0, ch, nbin, xb0);
+                    else if (B == 8) tc_frame_sums<8>(a, S, r, row0, ch, nbin, xb0);
+                    else if (B == 4) tc_frame_sums<4>(a, S, r, row0, ch, nbin, xb0);
+                    else tc_frame_sums<2>(a, S, r, row0, ch, nbin, xb0);
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
             }
@@ -342,6 +386,6 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-inline size_t blockdft_tc_smem_bytes() { return (size_t)TC_STAGES * TC_STAGE_BYTES + 3 * TC_STAGES * 8 + 16 + 1024; }
+inline size_t blockdft_tc_smem_bytes() { return (size_t)TC_STAGES * TC_STAGE_BYTES + (3 * TC_STAGES + 1) * 8 + 16 + 1024; }
 
 }  // namespace o4

@@ -1056,7 +1056,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 const long long grid = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
                 if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
                 Bracket b(p, s, timing, "blockdft_tc_gemm");
-                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS + 32, smem, s>>>(g);
+                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS + 64, smem, s>>>(g);
                 CK(cudaGetLastError());
             } else {
                 BlockDftGemmArgs g;
