@@ -53,6 +53,14 @@ extern "C" {
                                                     of the tensor cores (tcgen05 kind::tf32, 3xTF32 split precision) */
 #define OMEGA4_FLAG_TENSOR 32                    /* force the tensor-core GEMM when the plan default is off (OMEGA4_TENSOR=0) */
 
+/* Environment knobs read by the library (developer / A-B measurement; defaults are the product path):
+     OMEGA4_BLOCKDFT_FD=1       plan build: cosine-sum (frequency-domain) windowing for every hop-block resolution
+                                instead of the exact-windowing GEMM operand
+     OMEGA4_BLOCKDFT_UNFUSED=1  plan build: write the GEMM result Q and assemble frames in a separate kernel
+     OMEGA4_KW_F64=1            per call: float64-state K-weighting kernel instead of the float32-state one
+     OMEGA4_TENSOR=0            plan build: hop-block GEMM on the CUDA cores unless OMEGA4_FLAG_TENSOR is passed
+     OMEGA4_HOST_CHUNK_MB=n     plan build: device bytes per slot of the host-buffer pipeline (default 1024) */
+
 #define OMEGA4_FLAG_SERIAL_STATS 64               /* keep the deque-statistics kernel on the caller's stream (default: it
                                                     runs on an internal side stream underneath the FFT kernels) */
 

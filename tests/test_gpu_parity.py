@@ -286,6 +286,39 @@ def test_blockdft_96k_default_and_window_variants(golden):
             os.environ.pop("OMEGA4_BLOCKDFT_FD", None)
 
 
+def test_alternate_kernel_paths_stay_covered(golden):
+    """The developer knobs select kernels the default path no longer runs: the float64-state K-weighting kernel in
+    batch mode (OMEGA4_KW_F64=1) and the unfused frame assembly of the exact-windowing GEMM
+    (OMEGA4_BLOCKDFT_UNFUSED=1, blockdft_sum_kernel).  Both must agree with the default path and the fixtures."""
+    from omega4_b200 import _native as N
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
+    g = golden("multires_baseline.npz")
+    x = g["x"][None, : 120 * HOP]
+    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
+    base = p.analyze_host(x, want_series=True, flags=N.FLAG_TIME_KERNELS)
+    os.environ["OMEGA4_KW_F64"] = "1"
+    try:
+        f64 = p.analyze_host(x, want_series=True)
+    finally:
+        os.environ.pop("OMEGA4_KW_F64", None)
+    m = np.isfinite(base["lufs_inst"][0]) & (base["lufs_inst"][0] > -99)
+    assert m.sum() > 50
+    assert np.abs(f64["lufs_inst"][0][m] - base["lufs_inst"][0][m]).max() < 2e-5      # float32 vs float64 state
+    assert np.array_equal(f64["combined"], base["combined"])
+    p.close()
+    os.environ["OMEGA4_BLOCKDFT_UNFUSED"] = "1"
+    try:
+        p2 = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
+        unf = p2.analyze_host(x, want_meters=False, flags=N.FLAG_TIME_KERNELS)
+        assert "blockdft_asm_8192" in _kernel_names(p2) and "blockdft_tc_gemm" in _kernel_names(p2)
+        p2.close()
+    finally:
+        os.environ.pop("OMEGA4_BLOCKDFT_UNFUSED", None)
+    # same GEMM, same additions in a different order: equal to float32 rounding of the frame sums
+    scale = base["combined"][0].max(axis=1, keepdims=True) + 1e-20
+    assert (np.abs(unf["combined"][0] - base["combined"][0]) / scale).max() < 2e-6
+
+
 # ------------------------------------------------------------------ section 8f rank 1: app post-processing
 TOL_BAR = 1e-5     # band_values live in [0, 1]; 0.01 dB on the spectrum is 5.8e-4 relative on a sqrt'd bar
 
