@@ -189,10 +189,16 @@ static int launch_kweight32(const Kweight32Args& a, cudaStream_t s) {
 }
 
 static int launch_stats(const StatsArgs& a, cudaStream_t s) {
-    const size_t smem = stats_smem_bytes();
-    CK(cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.n_ch <= 0) return OMEGA4_OK;
-    stats_kernel<<<a.n_ch, ST_THREADS, smem, s>>>(a);
+    if (a.fresh) {                                   // no carried state to sort: 14.7 KB per channel, 15 channels per SM
+        const size_t smem = stats_smem_bytes<false>();
+        CK(cudaFuncSetAttribute(stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stats_kernel<false><<<a.n_ch, ST_THREADS, smem, s>>>(a);
+    } else {
+        const size_t smem = stats_smem_bytes<true>();
+        CK(cudaFuncSetAttribute(stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stats_kernel<true><<<a.n_ch, ST_THREADS, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
     return OMEGA4_OK;
 }

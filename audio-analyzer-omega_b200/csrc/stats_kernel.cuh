@@ -86,17 +86,23 @@ __device__ __forceinline__ double st_percentile_f(const float* s, int n, double 
 
 // ONE WARP PER CHANNEL, no block barriers.  The per-frame values are rounded to float32 on entry
 // (the outputs are float32; 4e-6 LU) and every sum adds and subtracts exactly those rounded values
-// in double, so nothing drifts.  Shared memory per channel: ring of the last 3600 values, sorted
-// gated copy (4096 slots for the one-off bitonic sort of carried state), ring of the last 60 peaks
-// = 31 KB -> 7 channels resident per SM.
-constexpr int STW_SMEM = (ST_I + ST_SORT + 64) * (int)sizeof(float);
+// in double, so nothing drifts.  Shared memory per channel: the sorted gated copy and the ring of the last
+// 60 peaks only -- the window itself is never kept on chip: the value that expires from the 3600 / 180 / 24
+// windows at hop k is the value pushed that many hops earlier, i.e. an element of the input series (or of
+// the carried state), fetched one 32-hop slice ahead with the new values.  14.7 KB per channel -> 15 channels
+// per SM: BASELINE's 2048 channels are resident in ONE wave (the kernel is a latency-bound sequential walk,
+// its duration is hops x per-hop latency x waves; with the ring on chip it needed 31 KB and two waves, and
+// squeezed the FFT kernels it overlaps out of shared memory).  CARRIED = state from an earlier call has to be
+// sorted once: 4096 slots for the bitonic network (16.6 KB).
+template <bool CARRIED>
+constexpr int stw_smem() { return ((CARRIED ? ST_SORT : ST_I) + 64) * (int)sizeof(float); }
 
+template <bool CARRIED>
 __global__ void __launch_bounds__(32)
 stats_kernel(const __grid_constant__ StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* win = reinterpret_cast<float*>(smem_raw);          // ring of the last 3600 values
-    float* srt = win + ST_I;                                  // sorted gated values
-    float* pkw = srt + ST_SORT;                               // ring of the last 60 peaks
+    float* srt = reinterpret_cast<float*>(smem_raw);          // sorted gated values
+    float* pkw = srt + (CARRIED ? ST_SORT : ST_I);            // ring of the last 60 peaks
 
     const int ch = blockIdx.x;
     const int lane = threadIdx.x;
@@ -107,7 +113,7 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
 
     int n_hist = 0, n_tp = 0;
     double cur[5] = {-100.0, -100.0, -100.0, 0.0, -100.0};
-    if (!a.fresh) {
+    if (CARRIED && !a.fresh) {
         n_hist = (int)st[0];
         n_tp = (int)st[1];
         if (n_hist > 0 || n_tp > 0 || st[7] != 0.0) {
@@ -115,16 +121,17 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
             for (int i = 0; i < 5; ++i) cur[i] = st[2 + i];
         }
     }
-    for (int i = lane; i < n_hist; i += 32) win[i] = (float)st[8 + i];
-    for (int i = lane; i < n_tp; i += 32) pkw[i] = (float)st[8 + ST_I + i];
+    const int n0 = n_hist;                                    // carried window length (oldest first in st[8 ..])
+    const double* win0 = st + 8;
+    if (CARRIED) for (int i = lane; i < n_tp; i += 32) pkw[i] = (float)st[8 + ST_I + i];
     __syncwarp();
     // all lanes keep the same (uniform) bookkeeping
-    int head = 0, pk_head = 0, ns = 0, cnt_m = 0, cnt_s = 0;
+    int pk_head = 0, ns = 0, cnt_m = 0, cnt_s = 0;
     double sum_i = 0.0, sum_m = 0.0, sum_s = 0.0, inv_m = 1.0, inv_s = 1.0, inv_ns = 0.0;
     float tp_max = -CUDART_INF_F;
-    if (n_hist > 0 || n_tp > 0) {                             // carried state: rebuild the derived structures
+    if (CARRIED && (n_hist > 0 || n_tp > 0)) {                // carried state: rebuild the derived structures
         for (int i = lane; i < ST_SORT; i += 32) {
-            float v = (i < n_hist) ? win[i] : CUDART_INF_F;
+            float v = (i < n_hist) ? (float)win0[i] : CUDART_INF_F;
             srt[i] = (v > gate) ? v : CUDART_INF_F;           // non-gated entries sort to the end
         }
         __syncwarp();
@@ -142,14 +149,14 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
             }
         }
         double si = 0.0; int c = 0;
-        for (int i = lane; i < n_hist; i += 32) { float v = win[i]; if (v > gate) { ++c; si += (double)v; } }
+        for (int i = lane; i < n_hist; i += 32) { float v = (float)win0[i]; if (v > gate) { ++c; si += (double)v; } }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
         ns = c; sum_i = si;
         cnt_m = n_hist < ST_M ? n_hist : ST_M;
         cnt_s = n_hist < ST_S ? n_hist : ST_S;
-        for (int i = n_hist - cnt_m; i < n_hist; ++i) sum_m += (double)win[i];
-        for (int i = n_hist - cnt_s; i < n_hist; ++i) sum_s += (double)win[i];
+        for (int i = n_hist - cnt_m; i < n_hist; ++i) sum_m += (double)(float)win0[i];
+        for (int i = n_hist - cnt_s; i < n_hist; ++i) sum_s += (double)(float)win0[i];
         if (cnt_m > 0) inv_m = 1.0 / (double)cnt_m;
         if (cnt_s > 0) inv_s = 1.0 / (double)cnt_s;
         if (ns > 0) inv_ns = 1.0 / (double)ns;
@@ -167,19 +174,33 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
         for (int i = 0; i < 5; ++i) orow[i] = (float)cur[i];
     }
 
-    float my_l = 0.f, my_t = 0.f;                              // lane i holds hop kb + i of the current 32-hop slice
+    // the value pushed D pushes before push p of this call: an element of the series, or of the carried window
+    auto pushed_before = [&](int p, int D) -> float {
+        const int q = p - D;
+        if (q >= 0) return (float)lufs[kbeg + q];
+        const int c = n0 + q;
+        return (CARRIED && c >= 0) ? (float)win0[c] : 0.f;
+    };
+    float my_l = 0.f, my_t = 0.f, my_oi = 0.f, my_os = 0.f, my_om = 0.f;   // lane i holds hop kb + i of the current 32-hop slice
     for (int k = kbeg; k < a.n_frames; ++k) {
         const int kk = (k - kbeg) & 31;
         if (kk == 0) {
             const int idx = k + lane;
-            my_l = idx < a.n_frames ? (float)lufs[idx] : 0.f;
-            my_t = idx < a.n_frames ? (float)tps[idx] : 0.f;
+            const bool ok = idx < a.n_frames;
+            my_l = ok ? (float)lufs[idx] : 0.f;
+            my_t = ok ? (float)tps[idx] : 0.f;
+            my_oi = ok ? pushed_before(idx - kbeg, ST_I) : 0.f;          // leaves the 3600 window at this hop
+            my_os = ok ? pushed_before(idx - kbeg, ST_S) : 0.f;          // leaves the 180 window
+            my_om = ok ? pushed_before(idx - kbeg, ST_M) : 0.f;          // leaves the 24 window
         }
         const float nv = __shfl_sync(0xffffffffu, my_l, kk);
         const float ntp = __shfl_sync(0xffffffffu, my_t, kk);
+        const float ov_i = __shfl_sync(0xffffffffu, my_oi, kk);
+        const float ov_s = __shfl_sync(0xffffffffu, my_os, kk);
+        const float ov_m = __shfl_sync(0xffffffffu, my_om, kk);
         // ---- expiring value, positions in the sorted gated array
         const bool has_old = (n_hist == ST_I);
-        const float ov = has_old ? win[head] : 0.f;
+        const float ov = has_old ? ov_i : 0.f;
         const bool rem = has_old && (ov > gate);
         const bool ins = (nv > gate);
         const int prem = rem ? warp_lower_bound(srt, ns, ov, lane) : -1;
@@ -193,31 +214,30 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
         else if (pins >= 0) { lo = pins; hi = ns - 1; }
         const bool left = (prem >= 0 && (pins < 0 || pins > prem));
         if (hi >= lo) {
-            if (left) {                                       // ascending batches of 128: read, sync, write one lower
-                for (int base = lo; base <= hi; base += 128) {
-                    float t4[4];
+            constexpr int SB = 8;                                 // elements per lane and batch
+            if (left) {                                       // ascending batches of 256: read, sync, write one lower
+                for (int base = lo; base <= hi; base += 32 * SB) {
+                    float tb[SB];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { int idx = base + lane + 32 * j; if (idx <= hi) t4[j] = srt[idx]; }
+                    for (int j = 0; j < SB; ++j) { int idx = base + lane + 32 * j; if (idx <= hi) tb[j] = srt[idx]; }
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { int idx = base + lane + 32 * j; if (idx <= hi) srt[idx - 1] = t4[j]; }
+                    for (int j = 0; j < SB; ++j) { int idx = base + lane + 32 * j; if (idx <= hi) srt[idx - 1] = tb[j]; }
                 }
             } else {                                          // descending batches: read, sync, write one higher
-                for (int top = hi; top >= lo; top -= 128) {
-                    float t4[4];
+                for (int top = hi; top >= lo; top -= 32 * SB) {
+                    float tb[SB];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { int idx = top - lane - 32 * j; if (idx >= lo) t4[j] = srt[idx]; }
+                    for (int j = 0; j < SB; ++j) { int idx = top - lane - 32 * j; if (idx >= lo) tb[j] = srt[idx]; }
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { int idx = top - lane - 32 * j; if (idx >= lo) srt[idx + 1] = t4[j]; }
+                    for (int j = 0; j < SB; ++j) { int idx = top - lane - 32 * j; if (idx >= lo) srt[idx + 1] = tb[j]; }
                 }
             }
         }
         __syncwarp();
         // ---- uniform bookkeeping + single-lane stores
-        int slot;
-        if (has_old) { slot = head; head = (head + 1 == ST_I) ? 0 : head + 1; }
-        else { slot = n_hist; ++n_hist; }
+        if (!has_old) ++n_hist;
         const int ns_new = ns + (ins ? 1 : 0) - (rem ? 1 : 0);
         if (rem) sum_i -= (double)ov;
         if (ins) sum_i += (double)nv;
@@ -225,19 +245,18 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
         ns = ns_new;
         if (ns == 0) sum_i = 0.0;
         sum_m += (double)nv;
-        if (cnt_m == ST_M) { int j = slot - ST_M; if (j < 0) j += ST_I; sum_m -= (double)win[j]; }
+        if (cnt_m == ST_M) sum_m -= (double)ov_m;
         else { ++cnt_m; inv_m = 1.0 / (double)cnt_m; }
         sum_s += (double)nv;
-        if (cnt_s == ST_S) { int j = slot - ST_S; if (j < 0) j += ST_I; sum_s -= (double)win[j]; }
+        if (cnt_s == ST_S) sum_s -= (double)ov_s;
         else { ++cnt_s; inv_s = 1.0 / (double)cnt_s; }
         int pslot;
         float otp = -CUDART_INF_F;
         if (n_tp == ST_P) { pslot = pk_head; otp = pkw[pk_head]; pk_head = (pk_head + 1 == ST_P) ? 0 : pk_head + 1; }
         else { pslot = n_tp; ++n_tp; }
-        __syncwarp();                                         // every lane has read win[j], pkw[pk_head], win[head]
+        __syncwarp();                                         // every lane has read pkw[pk_head]
         if (lane == 0) {
             if (ins) srt[pins - ((prem >= 0 && pins > prem) ? 1 : 0)] = nv;
-            win[slot] = nv;
             pkw[pslot] = ntp;
         }
         __syncwarp();
@@ -265,15 +284,38 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
         }
     }
     __syncwarp();
-    // ---- write state back (chronological order)
-    for (int i = lane; i < n_hist; i += 32) st[8 + i] = (double)win[(n_hist == ST_I) ? (head + i) % ST_I : i];
-    for (int i = lane; i < n_tp; i += 32) st[8 + ST_I + i] = (double)pkw[(n_tp == ST_P) ? (pk_head + i) % ST_P : i];
+    // ---- write state back (chronological order): the last n_hist entries of (carried window ++ this call's pushes).
+    // In place: entry i comes from combined index c = i + shift >= i, so ascending 32-wide batches never read a
+    // slot an earlier batch has overwritten.
+    {
+        const int P = a.n_frames - kbeg;                      // pushes of this call
+        const int shift = n0 + P - n_hist;
+        for (int b0 = 0; b0 < n_hist; b0 += 32) {
+            const int i = b0 + lane;
+            double v = 0.0;
+            if (i < n_hist) {
+                const int c = i + shift;
+                v = (c < n0) ? (double)(float)win0[c] : (double)(float)lufs[kbeg + c - n0];
+            }
+            __syncwarp();
+            if (i < n_hist) st[8 + i] = v;
+        }
+    }
+    {
+        float pv2[2] = {0.f, 0.f};                            // the peak ring has 60 entries: two per lane, read before any store
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { const int i = lane + 32 * j; if (i < n_tp) pv2[j] = pkw[(n_tp == ST_P) ? (pk_head + i) % ST_P : i]; }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { const int i = lane + 32 * j; if (i < n_tp) st[8 + ST_I + i] = (double)pv2[j]; }
+    }
     if (lane == 0) {
         st[0] = (double)n_hist; st[1] = (double)n_tp; st[7] = 1.0;
         st[2] = cur[0]; st[3] = cur[1]; st[4] = cur[2]; st[5] = cur[3]; st[6] = cur[4];
     }
 }
 
-inline size_t stats_smem_bytes() { return (size_t)STW_SMEM; }
+template <bool CARRIED>
+inline size_t stats_smem_bytes() { return (size_t)stw_smem<CARRIED>(); }
 
 }  // namespace o4

@@ -144,6 +144,7 @@ def main():
                     help="config2 (default, the metric's configuration): 48 kHz stereo, 8192/4096/2048/1024; "
                          "config5: 96 kHz 8-channel (7.1) streams, six resolutions 32768 .. 1024 (BASELINE configs[4] shape; "
                          "an extra workload, reported with its own config.workload string)")
+    ap.add_argument("--flags", type=int, default=0, help="extra omega4_analyze flags (developer A/B runs, e.g. 64 = OMEGA4_FLAG_SERIAL_STATS)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -192,7 +193,7 @@ def main():
         torch.cuda.synchronize()
 
     def step(flags=0):
-        plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=flags | N.FLAG_FRESH_METERS)
+        plan.analyze_device(x, n_hops, 0, combined=comb, meters=met, flags=flags | args.flags | N.FLAG_FRESH_METERS)
 
     for _ in range(args.warmup):
         step()
