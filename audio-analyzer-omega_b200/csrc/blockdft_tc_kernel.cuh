@@ -38,9 +38,10 @@ constexpr int TC_STAGES = 4;
 #ifndef TC_EXPERIMENT_KS
 #define TC_EXPERIMENT_KS 2          // timing experiments only: 1 issues half of the MMAs (wrong results)
 #endif
-#ifndef TC_PG
-#define TC_PG 4                     // producer groups = chunks produced side by side (divides 8 warps)
-#endif
+// producer groups = chunks produced side by side.  Must equal TC_STAGES: a group then owns one stage and sees
+// every phase of its mbarriers; with any other ratio a group visits a stage only now and then and the parity
+// wait can mistake an older phase for the one it needs (tried: 4 groups x 3 stages dead-locks).
+#define TC_PG TC_STAGES
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;     // 8 / 16 KB per (hi | lo)
 constexpr int TC_B_BYTES = TC_BN * TC_KC * 4;     // 16 / 8 KB per (hi | lo)
