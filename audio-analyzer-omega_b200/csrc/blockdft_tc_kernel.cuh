@@ -1,14 +1,14 @@
 // blockdft_tc_kernel.cuh -- the hop-block partial DFT GEMM of blockdft_kernel.cuh on the 5th-gen
 // tensor cores: tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, 3xTF32 split precision.
 //
-//   Q[blocks x cols] = X[blocks x hop] . E[hop x cols]            (cols <= 512: both N-halves of TMEM)
+//   Q[blocks x cols] = X[blocks x hop] . E[hop x cols]            (cols <= 1024: up to four 256-column tiles)
 //
 // TF32 keeps 11 significant bits, far too few for the 0.01 dB parity bar next to strong peaks, so
 // both operands are split exactly,  x = x_hi + x_lo,  e = e_hi + e_lo  (hi = the top 11 bits, lo = the
 // remainder, itself rounded to TF32 by the hardware), and three products are accumulated in fp32:
 //   x_hi e_hi + x_hi e_lo + x_lo e_hi        (the dropped x_lo e_lo term is 2^-22 relative)
 // which restores ~fp32 accuracy at 3x the tensor work -- still several times cheaper than the CUDA-core
-// GEMM or the FFT for the resolutions that need <= 512 columns.  The tensor-core accumulator truncates
+// GEMM or the FFT for the resolutions that need <= 1024 columns.  The tensor-core accumulator truncates
 // instead of rounding (measured: error grows linearly with the number of accumulation steps), so the
 // large x_hi e_hi products and the 2^-11 smaller cross products go to SEPARATE TMEM accumulators and
 // are added once, in registers, in the epilogue: the main accumulator then sees 64 steps, not 192.
@@ -16,12 +16,14 @@
 // One CTA = 128 hop blocks x 256 columns (TC_MH = 1; or 256 x 128 with TC_MH = 2); TMEM: [main | cross]
 // x 256 columns = all 512.  K in chunks of 16 samples.  Shared-memory operand tiles use the canonical K-major SWIZZLE_64B layout
 // (8-row groups of 64-byte rows, 16-byte chunk index XOR (row >> 1) & 3, SBO = 512 B):
-//   A_hi / A_lo: written by all 256 threads (LDG.128 of the raw samples, split, STS.128)
+//   A_hi / A_lo: written by four producer groups of two warps, one chunk in flight per group
+//                (LDG.128 of the raw samples, split, STS.128, fence.proxy.async, one arrive per warp)
 //   B_hi / B_lo: the constant E table, pre-swizzled on the host into per-chunk byte images and
 //                fetched with one-dimensional cp.async.bulk (TMA without a tensor map) + mbarrier tx
-// A ninth warp's lane 0 requests the B images and issues the MMAs (12 per chunk), committing them to
-// the stage's mbarrier; the 256 producer threads run ahead by up to STAGES chunks (no block-wide
-// barrier in the main loop).  Epilogue: tcgen05.ld 32x32b -> registers (main + cross) -> Q.
+// Warp 8's lane 0 issues the MMAs (6 per chunk) and commits them to the stage's mbarrier; warp 9's lane 0
+// requests the B images as stages retire (no block-wide barrier in the main loop).
+// Epilogue: tcgen05.ld 32x32b -> registers (main + cross), then either Q as it is, or (exact-windowing operand)
+// the frame sums X_f[k] = sum_b Q_{f+1-B+b}[k][b] through shared memory -> X[ch][bin][frame].
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
