@@ -328,8 +328,20 @@ def main():
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
+            # nominal arithmetic of the kernel per channel-hop (5 N log2 N per complex FFT, FMA = 2): the compute-side
+            # view of the same kernel, next to the HBM view the contract asks for
+            kflop = {"true_peak": 2 * 5 * 2048 * 11 + 3 * 2048 * 6, "kweight_lufs": 4 * 2080 * 14,
+                     "multires_fft_2048": 5 * 1024 * 10 + 1024 * 12 + 2048, "multires_fft_1024": 5 * 512 * 9 + 512 * 12 + 1024,
+                     "multires_fft_4096": 5 * 2048 * 11 + 2048 * 12 + 4096, "multires_fft_8192": 5 * 4096 * 12 + 4096 * 12 + 8192}.get(dom)
+            fp32 = None
+            if kflop:
+                tf = ch_hops * kflop / (ktimes[dom] / 1e3) / 1e12
+                fp32 = {"flop_per_channel_hop": kflop, "achieved_tflops": tf, "peak_tflops_measured": FP32_PEAK_TFLOPS,
+                        "frac": tf / FP32_PEAK_TFLOPS,
+                        "note": "FFT butterflies are additions, not FMAs: at 100 % issue this instruction mix reaches about half the FMA peak; "
+                                "ncu smsp__issue_active of this kernel is 69 % (profiles/)"}
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_kind, "kernel_ms": ktimes[dom],
+                    "traffic": traffic, "peak_source": peak_kind, "kernel_ms": ktimes[dom], "fp32": fp32,
                     "kernel_share_of_step": ktimes[dom] / sum(ktimes.values()),
                     "note": "fp32-issue bound by arithmetic (about 220 FLOP per compulsory byte): low HBM fraction is expected; "
                             "kernel_share_of_step is of the summed kernel times (the statistics kernel overlaps the FFT kernels)"}
