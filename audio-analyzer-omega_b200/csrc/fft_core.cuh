@@ -349,6 +349,9 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
 #pragma unroll
             for (int k = 0; k < 16; ++k) Xq[17 * p + k] = v[k];
             __syncwarp();
+            // zaddr(q + 16 (p + G2 i) + 256 pq) = zq + 16 G2 i + 256 pq: the swizzle term depends on p and q only
+            // (q < 16 fills bits 0-3, p the next log2 G2 bits), so the bit arithmetic is done once per thread
+            const int zq = zaddr<LOG2M>(q + 16 * p);
 #pragma unroll
             for (int i = 0; i < 16 / G2; ++i) {
                 const int k = p + G2 * i;
@@ -360,7 +363,7 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
                 if (G2 == 16) bf16pt(v);
                 if (!KEEP_LAST_IN_REGS) {
 #pragma unroll
-                    for (int pq = 0; pq < G2; ++pq) Z[zaddr<LOG2M>(q + 16 * k + 256 * pq)] = v[i * G2 + pq];
+                    for (int pq = 0; pq < G2; ++pq) Z[zq + 16 * G2 * i + 256 * pq] = v[i * G2 + pq];
                 }
             }
         }

@@ -41,9 +41,9 @@ struct MultiresArgs {
     int need_lo, need_cnt;     // FFT bins [need_lo, need_lo + need_cnt) feed the combine step
 };
 
-struct ZPadded { __device__ static __forceinline__ int at(int i) { return padi(i); } };
+struct ZPadded { static constexpr bool PADDED = true; __device__ static __forceinline__ int at(int i) { return padi(i); } };
 template <int LOG2M>
-struct ZSwizzled { __device__ static __forceinline__ int at(int i) { return zaddr<LOG2M>(i); } };
+struct ZSwizzled { static constexpr bool PADDED = false; __device__ static __forceinline__ int at(int i) { return zaddr<LOG2M>(i); } };
 
 // Untangle + |X| * weight for the bins this thread owns: pairs u = t + i*TPF in [0, M/2), plus
 // u = M/2 handled by thread 0.  In fused mode (no mag/complex output) only the bins the combine
@@ -56,6 +56,8 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
     constexpr int M = S::M, TPF = S::TPF;
     const bool all_bins = (a.mag_out != nullptr) || (a.cplx_out != nullptr);
     const int need_hi = a.need_lo + a.need_cnt;
+    const int zt0 = ZA::at(t);
+    const int zm0 = (t == 0) ? (ZA::PADDED ? M + M / 16 : M) : ZA::at(M - t);
     float* mrow = a.mag_out ? a.mag_out + row * (M + 1) : nullptr;
     float2* crow = a.cplx_out ? a.cplx_out + row * (M + 1) : nullptr;
 #pragma unroll
@@ -69,8 +71,9 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
         float mk = 0.f, mm = 0.f;
         float2 Xk = make_float2(0.f, 0.f), Xm = Xk;
         if (active) {
-            const float2 Zk = Z[ZA::at(u)];
-            const float2 Zm = Z[ZA::at((M - u) & (M - 1))];
+            const float2 Zk = Z[(i < 8) ? zt0 + i * TPF + (ZA::PADDED ? i * (TPF / 16) : 0) : ZA::at(u)];   // at(t + i TPF) is linear in i
+            // mirrored bin: at(M - t - i TPF) = at(M - t) - i TPF (- i TPF / 16 when padded) for i >= 1; i = 0 wraps for t = 0
+            const float2 Zm = Z[(i >= 1 && i < 8) ? zm0 - i * TPF - (ZA::PADDED ? i * (TPF / 16) : 0) : ZA::at((M - u) & (M - 1))];
             const float2 w = twn[u];
             rfft_pair(Zk, Zm, w, Xk, Xm);
             if (all_bins || ink) { mk = cabs_fast(Xk); if (bw) mk *= bw[k]; }
@@ -90,6 +93,8 @@ template <int TPF>
 __device__ __forceinline__ void multires_combine(const MultiresArgs& a, const float* mags, int t, size_t row, bool active,
                                                  const CombTables tb) {
     float* orow = a.comb_out + row * a.T;
+    // single-owner target bins: (interp * weight) / weight of the reference's accumulate / normalise is interp to 1 ulp
+    const bool unit = (a.wnum == a.wden);
     for (int j = t; j < a.n_tb; j += TPF) {
         const int lo = tb.lo[j];
         float val = 0.f;
@@ -97,7 +102,7 @@ __device__ __forceinline__ void multires_combine(const MultiresArgs& a, const fl
             const float m0 = mags[lo - a.need_lo];
             const float m1 = mags[lo + 1 - a.need_lo];
             const float vi = fmaf(m1 - m0, tb.frac[j], m0);
-            val = __fdividef(vi * a.wnum, a.wden);      // (interp * weight) / weight of :389-395, 2 ulp
+            val = unit ? vi : __fdividef(vi * a.wnum, a.wden);      // (interp * weight) / weight of :389-395
         }
         orow[tb.idx[j]] = val;
     }

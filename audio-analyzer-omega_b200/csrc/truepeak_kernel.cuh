@@ -91,6 +91,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
         return m;
     };
 
+    const int zt = zaddr<LOG2M>(t);
     // this thread's base delay factors R_p[t]
     const float2 rbase1 = __ldg(a.rot + t), rbase2 = __ldg(a.rot + M + t), rbase3 = __ldg(a.rot + 2 * M + t);
     // raw samples of a pair: v[j] = (a[t + j TPF], b[t + j TPF]); fetched one round ahead
@@ -150,7 +151,7 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
                     const int k = t + j * TPF;
                     float2 rk = cmul(rb, a.step[p - 1][j]);
                     if (j == 8 && t == 0) rk = make_float2(a.nyq[p - 1], 0.f);      // k = W/2
-                    const float2 s = cmul(Z[zaddr<LOG2M>(k)], rk);
+                    const float2 s = cmul(Z[zt + j * TPF], rk);       // zaddr(t + j TPF) = zaddr(t) + j TPF (TPF = 16 G2)
                     v[j] = make_float2(s.x, -s.y);                // conj: inverse transform by the forward kernel
                 }
             }
