@@ -102,19 +102,23 @@ truepeak_kernel(const __grid_constant__ TruePeakArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
         if (!(act_a || act_b)) return;
-        const long long off_a = (long long)ch * a.ch_stride + a.frame_off0 + (long long)fa * a.frame_stride;
-        const long long off_b = off_a + a.frame_stride;
+        // one 64-bit base per frame; the 16 loads of a frame are then immediate offsets j * TPF from it
+        const long long off_a = (long long)ch * a.ch_stride + a.frame_off0 + (long long)fa * a.frame_stride + t;
+        if (a.x_is_f64) {
+            const double* pa = reinterpret_cast<const double*>(a.x) + off_a;
+            const double* pb = pa + a.frame_stride;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = t + j * TPF;
-            if (a.x_is_f64) {
-                const double* px = reinterpret_cast<const double*>(a.x);
-                if (act_a) v[j].x = (float)px[off_a + n];
-                if (act_b) v[j].y = (float)px[off_b + n];
-            } else {
-                const float* px = reinterpret_cast<const float*>(a.x);
-                if (act_a) v[j].x = __ldg(px + off_a + n);
-                if (act_b) v[j].y = __ldg(px + off_b + n);
+            for (int j = 0; j < 16; ++j) {
+                if (act_a) v[j].x = (float)pa[j * TPF];
+                if (act_b) v[j].y = (float)pb[j * TPF];
+            }
+        } else {
+            const float* pa = reinterpret_cast<const float*>(a.x) + off_a;
+            const float* pb = pa + a.frame_stride;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (act_a) v[j].x = __ldg(pa + j * TPF);
+                if (act_b) v[j].y = __ldg(pb + j * TPF);
             }
         }
     };
