@@ -86,6 +86,50 @@ __device__ __forceinline__ void multires_epilogue(const MultiresArgs& a, const f
     }
 }
 
+// Fused-mode epilogue (no magnitude / complex outputs): only the bins the combine step reads.  Whether iteration i
+// touches a needed bin at all is decided per CTA from the uniform range (no divergent branches: the per-lane part is
+// two predicated stores), and the mirrored half is skipped entirely when the needed range lies in the lower half of
+// the spectrum (N = 2048: bins 43 .. 213 of 1025).
+template <int LOG2M, typename ZA>
+__device__ __forceinline__ void multires_epilogue_fused(const MultiresArgs& a, const float2* Z, float* mags, int t,
+                                                        bool active, const float2* twn, const float* bw) {
+    using S = FftShape<LOG2M>;
+    constexpr int M = S::M, TPF = S::TPF;
+    const int lo = a.need_lo, hi = a.need_lo + a.need_cnt;
+    const unsigned cnt = (unsigned)a.need_cnt;
+    const int zt0 = ZA::at(t);
+    const int zm0 = (t == 0) ? (ZA::PADDED ? M + M / 16 : M) : ZA::at(M - t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool anyk = ((i + 1) * TPF > lo) && (i * TPF < hi);                  // k  in [i TPF, (i+1) TPF)
+        const bool anym = (M - i * TPF >= lo) && (M - (i + 1) * TPF + 1 < hi);      // km in [M - (i+1) TPF + 1, M - i TPF]
+        if (!(anyk || anym)) continue;                                             // warp-uniform
+        const int u = t + i * TPF, km = M - u;
+        float mk = 0.f, mm = 0.f;
+        if (active) {                                                              // warp-uniform
+            const float2 Zk = Z[zt0 + i * TPF + (ZA::PADDED ? i * (TPF / 16) : 0)];
+            const float2 Zm = Z[(i >= 1) ? zm0 - i * TPF - (ZA::PADDED ? i * (TPF / 16) : 0) : ZA::at((M - u) & (M - 1))];
+            float2 Xk, Xm;
+            rfft_pair(Zk, Zm, twn[u], Xk, Xm);
+            if (anyk) { mk = cabs_fast(Xk); if (bw) mk *= bw[u]; }
+            if (anym) { mm = cabs_fast(Xm); if (bw) mm *= bw[km]; }
+        }
+        if ((unsigned)(u - lo) < cnt) mags[u - lo] = mk;
+        if ((unsigned)(km - lo) < cnt) mags[km - lo] = mm;
+    }
+    if (t == 0 && (unsigned)(M / 2 - lo) < cnt) {                                  // the self-paired bin k = M/2
+        float mk = 0.f;
+        if (active) {
+            const float2 Zh = Z[ZA::at(M / 2)];
+            float2 Xk, Xm;
+            rfft_pair(Zh, Zh, twn[M / 2], Xk, Xm);
+            mk = cabs_fast(Xk);
+            if (bw) mk *= bw[M / 2];
+        }
+        mags[M / 2 - lo] = mk;
+    }
+}
+
 // np.interp segments of combine_results_optimized evaluated from the smem strip of magnitudes.
 struct CombTables { const int* idx; const int* lo; const float* frac; };
 
@@ -203,9 +247,13 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
                 for (int j = 0; j < 16; ++j) v[j] = __ldg(px + t + j * TPF);
             }
         }
-        if (valid)
-            multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active,
-                                                       twn, bw);
+        if (valid) {
+            if (a.mag_out == nullptr && a.cplx_out == nullptr)
+                multires_epilogue_fused<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, active, twn, bw);
+            else
+                multires_epilogue<LOG2M, ZSwizzled<LOG2M>>(a, Z, (r & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + f, active,
+                                                           twn, bw);
+        }
     }
     if (a.comb_out) {
         group_sync<TPF>(g);
