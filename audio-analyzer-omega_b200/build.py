@@ -13,8 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "omega4_b200", "libomega4_cuda.so")
 SOURCES = ["omega4_cuda.cu"]
-HEADERS = ["bars_kernel.cuh", "blockdft_kernel.cuh", "blockdft_tc_kernel.cuh", "fft_core.cuh", "multires_kernel.cuh", "truepeak_kernel.cuh", "kweight_kernel.cuh",
-           "stats_kernel.cuh", "misc_kernels.cuh", os.path.join("..", "..", "include", "omega4_cuda.h")]
+
+
+def _headers():
+    """Every header the translation unit can include: csrc/*.cuh (globbed, so the list cannot drift) + the C ABI."""
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+        [os.path.join("..", "..", "include", "omega4_cuda.h")]
+
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -30,7 +36,7 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + _headers()]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -40,7 +40,8 @@ struct BarsArgs {
     float p_frac;
     float scale;               // 0.8
     int normalize_max;
-    float* state;              // [n_ch][1 + n_valid]: has_prev flag, previous bars; or nullptr
+    float* state;              // [n_ch][1 + n_valid]: has_prev flag, previous bars; or nullptr (written by the last segment)
+    const float* state_in;     // what segment 0 reads: `state`, or a copy of it when several segments run side by side
     int fresh;                 // ignore state contents on entry
     float* bars_out;           // [n_ch][n_hops][n_valid]
     float* peaks_out;          // same shape or nullptr (band values before smoothing)
@@ -90,7 +91,7 @@ bars_kernel(const __grid_constant__ BarsArgs a) {
 #pragma unroll
     for (int i = 0; i < MAXB; ++i) prev[i] = 0.f;
     if (seg == 0 && a.state && !a.fresh) {
-        const float* st = a.state + (size_t)ch * (1 + a.n_valid);
+        const float* st = (a.state_in ? a.state_in : a.state) + (size_t)ch * (1 + a.n_valid);
         has_prev = st[0] != 0.f;
 #pragma unroll
         for (int i = 0; i < MAXB; ++i) {
@@ -132,6 +133,8 @@ bars_kernel(const __grid_constant__ BarsArgs a) {
                 // (__reduce_max_sync) finds the maximum, a ballot its owner.  Each lane's candidates are
                 // sorted in registers (bitonic network over its 16 or 32 values) and parked as a descending
                 // list in its slice of the warp's row buffer, so the owner's next candidate is one LDS away.
+                // Slots past the end of the row are padded with -1 for the sort and enter the selection as bit
+                // pattern 0 (the bits of -1.f would beat every real value in the unsigned comparison).
                 float srt[NV];
 #pragma unroll
                 for (int i = 0; i < NV; ++i) srt[i] = (lane + 32 * i < a.T) ? v[i] : -1.f;
@@ -140,14 +143,14 @@ bars_kernel(const __grid_constant__ BarsArgs a) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) cand[i] = srt[i];
                 int ptr = 0;
-                unsigned lbits = __float_as_uint(cand[0]);
+                unsigned lbits = __float_as_uint(fmaxf(cand[0], 0.f));
                 float kth = 0.f, kth1 = 0.f;                          // sorted[p_lo], sorted[p_lo + 1]
                 for (int it = 1; it <= K; ++it) {
                     const unsigned wb = __reduce_max_sync(0xffffffffu, lbits);
                     const int wl = __ffs(__ballot_sync(0xffffffffu, lbits == wb)) - 1;
                     if (it == K - 1) kth1 = __uint_as_float(wb);
                     if (it == K) kth = __uint_as_float(wb);
-                    if (lane == wl) { ++ptr; lbits = ptr < nv ? __float_as_uint(cand[ptr]) : 0u; }
+                    if (lane == wl) { ++ptr; lbits = ptr < nv ? __float_as_uint(fmaxf(cand[ptr], 0.f)) : 0u; }
                 }
                 __syncwarp();
                 if (K == 1) kth1 = kth;

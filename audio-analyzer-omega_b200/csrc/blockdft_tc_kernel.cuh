@@ -69,6 +69,10 @@ struct BlockDftTcArgs {
     short gB[32];              // per 32-column group (n_halves * 8): block positions per bin (2, 4, 8, 16; 0 = unused group)
     short gX[32];              // per group: index of its first bin in [0, nkx)
     short gN[32];              // per group: bins present (<= 16 / B)
+    short gS[32];              // per group: frame shift.  A transform of more than 16 hop blocks (N / hop = 32, 64) spreads a
+                               // bin over N / hop / 16 groups of 16 positions; the group holding positions 16 p .. 16 p + 15
+                               // adds its partial sum to the frame that ends gS = N / hop - 16 (p + 1) blocks after the
+                               // group's own last row, always with atomicAdd (several groups feed one X element); -1 = plain group
 };
 constexpr int TC_XROW = 17;          // float2 row stride of the epilogue exchange strip (conflict free)
 
@@ -147,15 +151,16 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
 // b at column q B + b).  Task 0: the frame whose last hop block is local row r; task 1 (r < B - 1): the frame that
 // ends r + 1 rows past the tile.  Frames that lie wholly inside the tile are stored, the others added atomically.
 template <int B>
-__device__ __forceinline__ void tc_frame_sums(const BlockDftTcArgs& a, const float2* S, int r, int row0, int ch, int nbin, int xb0) {
+__device__ __forceinline__ void tc_frame_sums(const BlockDftTcArgs& a, const float2* S, int r, int row0, int ch, int nbin, int xb0,
+                                              int shift = -1) {
     constexpr int PER = 16 / B;
 #pragma unroll
     for (int task = 0; task < 2; ++task) {
         if (task == 1 && r >= B - 1) break;
         const int R = task == 0 ? r : 128 + r;
-        const long long f = (long long)a.j0 + row0 + R;   // frame index = index of its last hop block
+        const long long f = (long long)a.j0 + row0 + R + (shift > 0 ? shift : 0);   // frame index = index of its last hop block
         if (f < 0 || f >= a.n_frames) continue;
-        const bool whole = (R - B + 1 >= 0) && (R <= 127);
+        const bool whole = (R - B + 1 >= 0) && (R <= 127) && shift < 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             if (q >= nbin) break;
@@ -355,7 +360,7 @@ blockdft_tc_kernel(const __grid_constant__ BlockDftTcArgs a) {
 #else
                 if (B > 0) {
 #endif
-                    if (B == 16) tc_frame_sums<16>(a, S, r, row0, ch, nbin, xb0);
+                    if (B == 16) tc_frame_sums<16>(a, S, r, row0, ch, nbin, xb0, a.gS[gi]);
                     else if (B == 8) tc_frame_sums<8>(a, S, r, row0, ch, nbin, xb0);
                     else if (B == 4) tc_frame_sums<4>(a, S, r, row0, ch, nbin, xb0);
                     else tc_frame_sums<2>(a, S, r, row0, ch, nbin, xb0);

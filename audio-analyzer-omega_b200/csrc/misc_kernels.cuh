@@ -68,7 +68,8 @@ __global__ void band_map_kernel(const float* __restrict__ spec, int n_rows, int 
             val = comp ? sr[s] * comp[s] : sr[s];
         }
     }
-    if (db) val = 20.f * log10f(fmaxf(val, 1e-10f));
+    if (db == 1) val = 20.f * log10f(fmaxf(val, 1e-10f));           // panels/spectrogram_waterfall.py:85
+    else if (db == 2) val = 20.f * log10f(val + 1e-10f);             // plugins/panels/spectrogram.py:72
     out[gid] = val;
 }
 

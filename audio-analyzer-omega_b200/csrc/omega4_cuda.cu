@@ -24,6 +24,7 @@
 #include "multires_kernel.cuh"
 #include "stats_kernel.cuh"
 #include "truepeak_kernel.cuh"
+#include "waterfall_kernel.cuh"
 
 using namespace o4;
 
@@ -315,7 +316,7 @@ struct SparseSet {
     // windowing operand with 2 / 4 / 8 / 16 block positions per bin and 32-column aligned blocks
     bool fusable = false;
     int nkx = 0;                  // bins per frame over all resolutions of the set
-    short gB[32], gX[32], gN[32]; // per 32-column group of the GEMM: positions per bin, first bin, bins present
+    short gB[32], gX[32], gN[32], gS[32]; // per 32-column group of the GEMM: positions per bin, first bin, bins present, frame shift
     SparseSet() { for (int i = 0; i < OMEGA4_MAX_RES; ++i) of_res[i] = -1; }
     void release() {
         for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(sp[i].T); cudaFree(sp[i].kw); cudaFree(sp[i].tb_pos); }
@@ -487,9 +488,10 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
     if ((H % (tensor ? TC_KC : BD_KC)) != 0) return OMEGA4_OK;
     // tensor: up to four column tiles of 256 (each tile = all 512 TMEM columns as main | cross); CUDA cores: the widest tile
     const int max_cols = tensor ? 1024 : 128;
-    // exact (time-domain) windowing for the tensor-core set wherever a frame spans <= 16 hop blocks; longer
-    // transforms (config 5: 32768 / 16384 at hop 512) would need 64 / 32 column pairs per bin and keep the
-    // cosine-sum formulation.  OMEGA4_BLOCKDFT_FD=1 forces the cosine-sum formulation everywhere.
+    // exact (time-domain) windowing for the tensor-core set: one column pair per (bin, block position), up to 64
+    // hop blocks per frame (config 5: 32768 / 16384 at hop 512 take 2 x 2 x 64 + 2 x 8 x 32 = 768 columns).  The
+    // cosine-sum formulation loses up to 0.03 dB on a click under the window's near-zero edge and
+    // is only built on request: OMEGA4_BLOCKDFT_FD=1 forces it everywhere.
     const bool allow_td = tensor && !getenv("OMEGA4_BLOCKDFT_FD");
     int order[OMEGA4_MAX_RES];
     for (int r = 0; r < d->n_res; ++r) order[r] = r;
@@ -514,7 +516,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         const double two_pi = 6.283185307179586476925287;
         const int nk = (int)bins.size();
         const double fft_cost = 2.5 * N * (ri.log2m + 1);
-        if (allow_td && N / H <= 16 && (double)(2 * nk * (N / H)) * H <= 6.6 * fft_cost &&
+        if (allow_td && N / H <= 64 && (double)(2 * nk * (N / H)) * H <= 6.6 * fft_cost &&
             ((cols + 31) & ~31) + 2 * nk * (N / H) <= max_cols) {
             // ---- exact windowing: column pair (ki, b) = w[H b + n] e^{-2 pi i k (H b + n) / N}
             cols = (cols + 31) & ~31;                      // whole 32-column groups per resolution (fused epilogue)
@@ -635,14 +637,24 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
         int xo = 0;
         for (int si = 0; si < set->n; ++si) {
             SparseRes& sp = set->sp[si];
-            ok = ok && sp.td && (sp.B == 2 || sp.B == 4 || sp.B == 8 || sp.B == 16) && (sp.col0 % 32) == 0;
+            ok = ok && sp.td && (sp.B == 2 || sp.B == 4 || sp.B == 8 || sp.B == 16 || sp.B == 32 || sp.B == 64) && (sp.col0 % 32) == 0;
             sp.xoff = xo; xo += sp.nk;
         }
         set->nkx = xo;
-        for (int g = 0; g < 32; ++g) { set->gB[g] = 0; set->gX[g] = 0; set->gN[g] = 0; }
+        for (int g = 0; g < 32; ++g) { set->gB[g] = 0; set->gX[g] = 0; set->gN[g] = 0; set->gS[g] = -1; }
         if (ok)
             for (int si = 0; si < set->n; ++si) {
                 const SparseRes& sp = set->sp[si];
+                if (sp.B > 16) {                           // a bin spans B / 16 groups of 16 block positions each
+                    const int parts = sp.B / 16;
+                    for (int k0 = 0; k0 < sp.nk; ++k0)
+                        for (int pt = 0; pt < parts; ++pt) {
+                            const int g = (sp.col0 + 2 * (k0 * sp.B + 16 * pt)) / 32;
+                            set->gB[g] = 16; set->gX[g] = (short)(sp.xoff + k0); set->gN[g] = 1;
+                            set->gS[g] = (short)(sp.B - 16 * (pt + 1));
+                        }
+                    continue;
+                }
                 const int per = 16 / sp.B;                 // bins per 32-column group
                 for (int k0 = 0; k0 < sp.nk; k0 += per) {
                     const int g = (sp.col0 + 2 * k0 * sp.B) / 32;
@@ -1055,6 +1067,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 if (fusedx) {
                     g.X = (float2*)qbuf->p; g.n_frames = n_hops; g.nkx = set.nkx;
                     memcpy(g.gB, set.gB, sizeof g.gB); memcpy(g.gX, set.gX, sizeof g.gX); memcpy(g.gN, set.gN, sizeof g.gN);
+                    memcpy(g.gS, set.gS, sizeof g.gS);
                     CK(cudaMemsetAsync(qbuf->p, 0, qbytes, s));      // frames that straddle row tiles are completed with atomics
                 }
                 const size_t smem = blockdft_tc_smem_bytes();
@@ -1527,6 +1540,74 @@ extern "C" int omega4_band_map(int device, void* stream, int mem, const float* s
     return OMEGA4_OK;
 }
 
+extern "C" int omega4_waterfall(int device, void* stream, int mem, const float* spectra, int n_ch, int n_rows, int len,
+                                int lo, int hi, int db_form, int auto_gain, float gain_adjustment, float* state, int fresh,
+                                float* db_out, float* norm_out, float* rowstat_out) {
+    if (!spectra || n_ch < 0 || n_rows < 0 || len <= 0 || lo < 0 || hi <= lo || hi > len || (db_form != 0 && db_form != 1) ||
+        (!db_out && !norm_out && !rowstat_out))
+        return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    if (n_ch == 0 || n_rows == 0) return OMEGA4_OK;
+    if ((long long)n_ch * n_rows > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "too many rows for one waterfall call");
+    if (omega4_device_count() == 0) return fail(OMEGA4_ERR_NO_DEVICE, "no CUDA device visible: libomega4_cuda has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t rows = (size_t)n_ch * n_rows, n = (size_t)(hi - lo);
+    std::vector<void*> to_free;
+    auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
+#define CKF(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(OMEGA4_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(e__)); } } while (0)
+    WaterfallArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_ch = n_ch; a.n_rows = n_rows; a.len = len; a.lo = lo; a.hi = hi; a.db_form = db_form; a.auto_gain = auto_gain ? 1 : 0;
+    a.gain_adjustment = gain_adjustment;
+    const size_t st_bytes = (size_t)n_ch * WF_STATE * sizeof(float);
+    if (mem == OMEGA4_MEM_HOST) {
+        float* t = nullptr;
+        CKF(cudaMalloc(&t, rows * len * sizeof(float))); to_free.push_back(t);
+        CKF(cudaMemcpyAsync(t, spectra, rows * len * sizeof(float), cudaMemcpyHostToDevice, s));
+        a.spec = t;
+        if (db_out) { CKF(cudaMalloc(&a.db_out, rows * n * sizeof(float))); to_free.push_back(a.db_out); }
+        if (norm_out) { CKF(cudaMalloc(&a.norm_out, rows * n * sizeof(float))); to_free.push_back(a.norm_out); }
+        if (state) {
+            float* d_st = nullptr;
+            CKF(cudaMalloc(&d_st, st_bytes)); to_free.push_back(d_st);
+            if (!fresh) { CKF(cudaMemcpyAsync(d_st, state, st_bytes, cudaMemcpyHostToDevice, s)); a.state_in = d_st; }
+            a.state_out = d_st;
+        }
+    } else if (mem == OMEGA4_MEM_DEVICE) {
+        a.spec = spectra; a.db_out = db_out; a.norm_out = norm_out;
+        a.state_in = (state && !fresh) ? state : nullptr; a.state_out = state;
+    } else {
+        return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
+    }
+    if (mem == OMEGA4_MEM_DEVICE && rowstat_out) a.rowstat = rowstat_out;
+    else { CKF(cudaMalloc(&a.rowstat, rows * 4 * sizeof(float))); to_free.push_back(a.rowstat); }
+    waterfall_db_kernel<<<(unsigned)rows, 256, 0, s>>>(a);
+    CKF(cudaGetLastError());
+    waterfall_norm_kernel<<<(unsigned)rows, 256, 0, s>>>(a);
+    CKF(cudaGetLastError());
+    if (a.state_out) {
+        waterfall_state_kernel<<<(unsigned)((n_ch + 127) / 128), 128, 0, s>>>(a);
+        CKF(cudaGetLastError());
+    }
+    if (mem == OMEGA4_MEM_HOST) {
+        if (db_out) CKF(cudaMemcpyAsync(db_out, a.db_out, rows * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (norm_out) CKF(cudaMemcpyAsync(norm_out, a.norm_out, rows * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (rowstat_out) CKF(cudaMemcpyAsync(rowstat_out, a.rowstat, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (state) CKF(cudaMemcpyAsync(state, a.state_out, st_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    if (!to_free.empty()) CKF(cudaStreamSynchronize(s));
+    cleanup();
+#undef CKF
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_plan_set_gate_threshold(omega4_plan* p, double gate_threshold) {
+    if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
+    if (!(gate_threshold == gate_threshold)) return fail(OMEGA4_ERR_INVALID, "gate threshold is NaN");
+    p->gate = gate_threshold;
+    return OMEGA4_OK;
+}
+
 extern "C" int omega4_bass_bars(int device, void* stream, int mem, const float* magnitudes, int n_ch, int n_frames,
                                 int n_bins, const int* bar_bins, const float* comp, int n_bars, float* state,
                                 float* bars_out) {
@@ -1600,7 +1681,7 @@ struct omega4_bars {
     int device = 0, T = 0, n_valid = 0, p_lo = 0, normalize_max = 0;
     float p_frac = 0.f, scale = 0.8f;
     int* bands = nullptr; float* gain = nullptr; float* sf = nullptr; float* sfc = nullptr;
-    DevBuf h_spec, h_out, h_peak, h_state;
+    DevBuf h_spec, h_out, h_peak, h_state, state_in;
 };
 
 extern "C" omega4_bars* omega4_bars_create(const omega4_bars_desc* d, int device) {
@@ -1639,7 +1720,7 @@ extern "C" void omega4_bars_destroy(omega4_bars* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaFree(b->bands); cudaFree(b->gain); cudaFree(b->sf); cudaFree(b->sfc);
-    b->h_spec.release(); b->h_out.release(); b->h_peak.release(); b->h_state.release();
+    b->h_spec.release(); b->h_out.release(); b->h_peak.release(); b->h_state.release(); b->state_in.release();
     cudaGetLastError();
     delete b;
 }
@@ -1683,6 +1764,13 @@ extern "C" int omega4_bars_run(omega4_bars* b, void* stream, int mem, const floa
     a.seg = n_ch >= 1024 ? 4 * BARS_SEG : BARS_SEG;              // fewer warm-up replays when channels alone fill the GPU
     const long long grid = (long long)n_ch * ((n_hops + a.seg - 1) / a.seg);
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "bars grid too large");
+    if (a.state && !a.fresh && n_hops > a.seg) {
+        // the last segment of a channel writes the carried state while segment 0 of the same launch reads it:
+        // segment 0 reads a private copy
+        int rc = b->state_in.ensure(st_bytes); if (rc) return rc;
+        CK(cudaMemcpyAsync(b->state_in.p, a.state, st_bytes, cudaMemcpyDeviceToDevice, s));
+        a.state_in = (const float*)b->state_in.p;
+    }
     if (b->T <= 512) bars_kernel<16><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
     else bars_kernel<32><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
     CK(cudaGetLastError());

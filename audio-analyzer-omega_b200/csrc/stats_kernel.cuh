@@ -114,8 +114,9 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
     int n_hist = 0, n_tp = 0;
     double cur[5] = {-100.0, -100.0, -100.0, 0.0, -100.0};
     if (CARRIED && !a.fresh) {
-        n_hist = (int)st[0];
-        n_tp = (int)st[1];
+        // counts of a state vector the library did not write itself are clamped: they index shared memory
+        n_hist = min(max((int)st[0], 0), ST_I);
+        n_tp = min(max((int)st[1], 0), ST_P);
         if (n_hist > 0 || n_tp > 0 || st[7] != 0.0) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) cur[i] = st[2 + i];

@@ -29,7 +29,8 @@ FLAG_NO_BLOCKDFT = 8
 FLAG_NO_TENSOR = 16
 FLAG_TENSOR = 32
 FLAG_SERIAL_STATS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
+WATERFALL_STATE = 41
 
 #: every symbol include/omega4_cuda.h declares (checked by tests/test_abi_symbols.py)
 EXPORTS = (
@@ -38,6 +39,7 @@ EXPORTS = (
     "omega4_meter_frames", "omega4_meter_stats", "omega4_rfft_batch", "omega4_band_map",
     "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
     "omega4_analyze_s16", "omega4_plan_set_weighting", "omega4_bass_bars", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
+    "omega4_waterfall", "omega4_plan_set_gate_threshold",
 )
 
 
@@ -128,6 +130,10 @@ def lib() -> C.CDLL:
         l.omega4_rfft_batch.argtypes = [ip, vp, ip, vp, ip, ip, vp, vp, vp]
         l.omega4_band_map.restype = ip
         l.omega4_band_map.argtypes = [ip, vp, ip, vp, ip, ip, vp, ip, vp, vp, ip]
+        l.omega4_waterfall.restype = ip
+        l.omega4_waterfall.argtypes = [ip, vp, ip, vp, ip, ip, ip, ip, ip, ip, ip, C.c_float, vp, ip, vp, vp, vp]
+        l.omega4_plan_set_gate_threshold.restype = ip
+        l.omega4_plan_set_gate_threshold.argtypes = [vp, C.c_double]
         l.omega4_bass_bars.restype = ip
         l.omega4_bass_bars.argtypes = [ip, vp, ip, vp, ip, ip, ip, vp, vp, ip, vp, vp]
         l.omega4_synth_fill.restype = ip
@@ -177,6 +183,29 @@ def ptr(a) -> Optional[int]:
     if isinstance(a, int):
         return a
     raise TypeError(f"cannot take the address of {type(a)}")
+
+
+_DT = {"float32": 4, "float64": 8, "int16": 2, "int32": 4}
+
+
+def checked(a, dtype: str, n_elems: Optional[int] = None, what: str = "buffer") -> Optional[int]:
+    """Address of a numpy array / torch tensor after checking what the C side takes on trust: element type,
+    C-contiguity and (when given) the element count.  None passes through."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        ok_dt, contiguous, count = a.dtype == np.dtype(dtype), a.flags["C_CONTIGUOUS"], a.size
+    elif hasattr(a, "data_ptr"):
+        ok_dt, contiguous, count = str(a.dtype).endswith(dtype), a.is_contiguous(), a.numel()
+    else:
+        raise TypeError(f"{what}: cannot take the address of {type(a)}")
+    if not ok_dt:
+        raise Omega4CudaError(f"{what} must be {dtype}, got {a.dtype}")
+    if not contiguous:
+        raise Omega4CudaError(f"{what} must be C-contiguous")
+    if n_elems is not None and count < n_elems:
+        raise Omega4CudaError(f"{what} holds {count} elements, the call needs {n_elems}")
+    return ptr(a)
 
 
 def ptr_array(items: Sequence) -> "C.Array":

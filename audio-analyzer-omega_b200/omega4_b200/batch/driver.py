@@ -6,6 +6,13 @@ Replaces the caller side of the reference for this path -- ``process_audio_spect
 frame schedule of SURVEY.md section 7 step 2: hop 512; resolution N contributes to hop k once
 (k+1)*512 >= N; one meter update per hop on the Hann-windowed last 2048 samples.
 
+Which feed this is: the batch schedule hands every resolution the last N RAW samples at each 512-sample
+hop -- the feed of the reference's own headless driver ``benchmark_multi_fft`` (512-sample chunks into
+the rings).  The pygame application feeds differently: it passes the Hann-windowed 2048-sample window to
+``process_audio_chunk`` once per video frame (omega4_main.py:953-980), so its rings hold overlapping,
+pre-windowed blocks; that feed is reproduced by the streaming shim
+(``omega4_b200.audio.multi_resolution_fft.MultiResolutionFFT``, golden ``multires_appfeed.npz``), not here.
+
 ``StreamBatch`` keeps the per-channel carry between time tiles (the last max(N)-hop samples and
 the meters' deque state), so arbitrarily long streams can be processed tile by tile -- e.g. when
 the audio is generated on the device because it does not fit in host memory (BASELINE config 4).

@@ -118,6 +118,7 @@ class ProfessionalMetering:
             return self.current_lufs
         f = np.asarray(audio_data, dtype=np.float64)
         li, tp, _ = self._mode_plan().meter_frames_host(f)
+        self._plan.set_gate_threshold(self.gate_threshold)       # read on every call, as :267 does (plans are shared)
         out = self._plan.meter_stats_host(li, tp, state=self._state, fresh=self._fresh)
         self._fresh = False
         for k, v in zip(METER_KEYS, out[0, 0]):

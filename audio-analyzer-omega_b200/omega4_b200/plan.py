@@ -166,6 +166,22 @@ class AnalysisPlan:
         N.check(N.lib().omega4_plan_set_weighting(self.handle, C.byref(w)), "omega4_plan_set_weighting")
         self.weighting_mode = mode
 
+    def set_gate_threshold(self, gate_threshold: float = -70.0):
+        """ProfessionalMetering.gate_threshold (professional_meters.py:36, :267) for every later call."""
+        N.check(N.lib().omega4_plan_set_gate_threshold(self.handle, float(gate_threshold)), "omega4_plan_set_gate_threshold")
+
+    def _mag_ptrs(self, magnitudes, rows: int):
+        """Pointer table of the optional per-resolution magnitude outputs: exactly one entry per resolution
+        (None = not wanted), each float32, contiguous and large enough -- the C side indexes all n_res entries."""
+        if magnitudes is None:
+            return None
+        if len(magnitudes) != len(self.sizes):
+            raise N.Omega4CudaError(f"magnitudes needs {len(self.sizes)} entries (one per resolution), got {len(magnitudes)}")
+        arr = (C.c_void_p * len(self.sizes))()
+        for i, (m, n) in enumerate(zip(magnitudes, self.sizes)):
+            arr[i] = N.checked(m, "float32", rows * (n // 2 + 1), f"magnitudes[{i}]")
+        return arr
+
     # ------------------------------------------------------------------ helpers
     def first_hop(self, n: int, hist: int = 0) -> int:
         """First hop index at which a window of n samples is filled."""
@@ -206,8 +222,9 @@ class AnalysisPlan:
         tp = np.empty((n_ch, n_hops), np.float64) if want_series else None
         base = x.ctypes.data + hist_samples * 4
         rc = N.lib().omega4_analyze(self.handle, None, N.MEM_HOST, base, x.strides[0] // 4, n_ch, n_hops,
-                                    hist_samples, N.ptr(comb), N.ptr_array(mags) if mags else None, N.ptr(met),
-                                    N.ptr(li), N.ptr(tp), N.ptr(meter_state), flags)
+                                    hist_samples, N.ptr(comb), self._mag_ptrs(mags, n_ch * n_hops), N.ptr(met),
+                                    N.ptr(li), N.ptr(tp),
+                                    N.checked(meter_state, "float64", n_ch * N.METER_STATE_DOUBLES, "meter_state"), flags)
         N.check(rc, "omega4_analyze")
         out.update(combined=comb, magnitudes=mags, meters=met, lufs_inst=li, tp_db=tp)
         return out
@@ -221,10 +238,16 @@ class AnalysisPlan:
         n_ch = samples.shape[0]
         if stream is None:
             stream = torch.cuda.current_stream(samples.device).cuda_stream
+        if samples.shape[1] < hist_samples + n_hops * self.hop:
+            raise N.Omega4CudaError("samples rows are shorter than hist_samples + n_hops * hop")
+        rows = n_ch * n_hops
         base = samples.data_ptr() + hist_samples * 4
         rc = N.lib().omega4_analyze(self.handle, stream, N.MEM_DEVICE, base, samples.stride(0), n_ch, n_hops,
-                                    hist_samples, N.ptr(combined), N.ptr_array(magnitudes) if magnitudes else None,
-                                    N.ptr(meters), N.ptr(lufs_inst), N.ptr(tp_db), N.ptr(meter_state), flags)
+                                    hist_samples, N.checked(combined, "float32", rows * self.target_bins, "combined"),
+                                    self._mag_ptrs(magnitudes, rows),
+                                    N.checked(meters, "float32", rows * N.N_METERS, "meters"),
+                                    N.checked(lufs_inst, "float64", rows, "lufs_inst"), N.checked(tp_db, "float64", rows, "tp_db"),
+                                    N.checked(meter_state, "float64", n_ch * N.METER_STATE_DOUBLES, "meter_state"), flags)
         N.check(rc, "omega4_analyze")
 
     # ------------------------------------------------------------------ int16 wire format
@@ -261,9 +284,13 @@ class AnalysisPlan:
         if stream is None:
             stream = torch.cuda.current_stream(frames.device).cuda_stream
         base = frames.data_ptr() + hist_frames * n_interleaved * 2
+        rows = frames.shape[0] * n_interleaved * n_hops
         rc = N.lib().omega4_analyze_s16(self.handle, stream, N.MEM_DEVICE, base, frames.stride(0), frames.shape[0],
-                                        n_interleaved, n_hops, hist_frames, N.ptr(combined), None, N.ptr(meters),
-                                        None, None, N.ptr(meter_state), flags)
+                                        n_interleaved, n_hops, hist_frames,
+                                        N.checked(combined, "float32", rows * self.target_bins, "combined"), None,
+                                        N.checked(meters, "float32", rows * N.N_METERS, "meters"), None, None,
+                                        N.checked(meter_state, "float64", frames.shape[0] * n_interleaved * N.METER_STATE_DOUBLES,
+                                                  "meter_state"), flags)
         N.check(rc, "omega4_analyze_s16")
 
     # ------------------------------------------------------------------ pieces used by the shims
@@ -273,7 +300,7 @@ class AnalysisPlan:
             if m is not None and m.shape[1] != n // 2 + 1:
                 raise ValueError("magnitude length does not match the resolution")
         out = np.empty((n_rows, self.target_bins), np.float32)
-        rc = N.lib().omega4_combine(self.handle, None, N.MEM_HOST, N.ptr_array(mags), n_rows, N.ptr(out))
+        rc = N.lib().omega4_combine(self.handle, None, N.MEM_HOST, self._mag_ptrs(mags, n_rows), n_rows, N.ptr(out))
         N.check(rc, "omega4_combine")
         return out
 
@@ -301,7 +328,8 @@ class AnalysisPlan:
         n_ch, n = li.shape
         out = np.empty((n_ch, n, N.N_METERS), np.float32)
         rc = N.lib().omega4_meter_stats(self.handle, None, N.MEM_HOST, N.ptr(li), N.ptr(tp), n_ch, n, first_frame,
-                                        N.ptr(state), N.ptr(out), 1 if fresh else 0)
+                                        N.checked(state, "float64", n_ch * N.METER_STATE_DOUBLES, "meter state"),
+                                        N.ptr(out), 1 if fresh else 0)
         N.check(rc, "omega4_meter_stats")
         return out
 
@@ -323,7 +351,9 @@ def rfft_batch_host(frames: np.ndarray, window: Optional[np.ndarray], want_compl
 
 
 def band_map_host(spectrum: np.ndarray, bands: Sequence[Tuple[int, int]], comp: Optional[np.ndarray] = None,
-                  db: bool = False, device: int = 0) -> np.ndarray:
+                  db=False, device: int = 0) -> np.ndarray:
+    """``db``: False = linear bars; True / 1 = 20 log10(max(x, 1e-10)) (panels/spectrogram_waterfall.py:85);
+    2 = 20 log10(x + 1e-10) (plugins/panels/spectrogram.py:72)."""
     N.require_device()
     s = np.ascontiguousarray(spectrum, dtype=np.float32)
     if s.ndim == 1:
@@ -333,6 +363,6 @@ def band_map_host(spectrum: np.ndarray, bands: Sequence[Tuple[int, int]], comp: 
     c = None if comp is None else np.ascontiguousarray(comp, dtype=np.float32)
     out = np.empty((rows, len(b)), np.float32)
     rc = N.lib().omega4_band_map(device, None, N.MEM_HOST, N.ptr(s), rows, ln, N.ptr(b), len(b), N.ptr(c), N.ptr(out),
-                                 1 if db else 0)
+                                 int(db))
     N.check(rc, "omega4_band_map")
     return out

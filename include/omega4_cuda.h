@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define OMEGA4_ABI_VERSION 1
+#define OMEGA4_ABI_VERSION 2
 
 #define OMEGA4_OK 0
 #define OMEGA4_ERR_INVALID (-1)   /* bad argument */
@@ -119,6 +119,11 @@ typedef struct omega4_weighting {
 } omega4_weighting;
 int omega4_plan_set_weighting(omega4_plan* plan, const omega4_weighting* weighting);
 
+/* ProfessionalMetering.gate_threshold (professional_meters.py:36, read at :267 on every calculate_lufs):
+ * values <= gate_threshold are left out of the integrated loudness and the loudness range.  Takes effect
+ * from the next omega4_analyze / omega4_meter_stats call on this plan (the plan descriptor's value until then). */
+int omega4_plan_set_gate_threshold(omega4_plan* plan, double gate_threshold);
+
 /* The whole hot path over a batch: replaces, per channel and hop,
  *   MultiResolutionFFT.process_audio_chunk + combine_results_optimized (multi_resolution_fft.py:228,335)
  *   ProfessionalMetering.calculate_lufs on the Hann-windowed last 2048 samples (professional_meters.py:231)
@@ -175,9 +180,26 @@ int omega4_rfft_batch(int device, void* stream, int mem, const float* frames, in
 
 /* PrecomputedFrequencyMapper.map_spectrum_to_bars (freq_mapper.py:165-196): bar = mean(spectrum[s:e])
  * with optional compensation curve; bands [n_bars][2] HOST int32; comp [len] HOST or NULL.
- * db != 0 additionally converts 20*log10(max(x,1e-10)) (panels/spectrogram_waterfall.py:85). */
+ * db = 1 additionally converts 20*log10(max(x,1e-10)) (panels/spectrogram_waterfall.py:85),
+ * db = 2 converts 20*log10(x + 1e-10) (plugins/panels/spectrogram.py:72). */
 int omega4_band_map(int device, void* stream, int mem, const float* spectrum, int n_rows, int len,
                     const int* bands, int n_bars, const float* comp, float* bars_out, int db);
+
+/* SpectrogramWaterfall.update + _normalize_spectrum (omega4/panels/spectrogram_waterfall.py:71-121), data side:
+ * per row  dB = 20 log10(max(spectrum[lo:hi], 1e-10))  (db_form 0; db_form 1 = the plugin panel's
+ * 20 log10(x + 1e-10), plugins/panels/spectrogram.py:72), (max, min) of the row into the panel's peak history,
+ * with auto_gain current_peak / current_floor = 95th / 5th percentile of the last 20 maxima / minima, then
+ * clip((dB + gain_adjustment - floor) / (peak - floor), 0, 1) (zeros when peak <= floor).
+ *   spectra     [n_ch][n_rows][len] magnitudes, rows in time order
+ *   state       [n_ch][OMEGA4_WATERFALL_STATE] float32 carried between calls (the last 19 (max, min) pairs, their
+ *               count, current_peak, current_floor), or NULL; fresh != 0 ignores its contents on entry
+ *               (a new panel: no history, peak 0, floor -80, :38-39)
+ *   db_out, norm_out  [n_ch][n_rows][hi - lo] or NULL;  rowstat_out [n_ch][n_rows][4] = row max dB, row min dB,
+ *               current_peak, current_floor after the row, or NULL */
+#define OMEGA4_WATERFALL_STATE 41
+int omega4_waterfall(int device, void* stream, int mem, const float* spectra, int n_ch, int n_rows, int len,
+                     int lo, int hi, int db_form, int auto_gain, float gain_adjustment, float* state, int fresh,
+                     float* db_out, float* norm_out, float* rowstat_out);
 
 /* BassZoomPanel._process_bass_detail_internal (omega4/panels/bass_zoom.py:141-214) after its 8192-point
  * FFT (omega4_rfft_batch), without the wall-clock peak hold: per bar mean(|X|[first .. first+count)) * comp,

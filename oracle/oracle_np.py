@@ -54,6 +54,16 @@ BASELINE_CONFIGS = (
     ((1000, 5000), 2048, 256, 1.0),
     ((5000, 20000), 1024, 256, 1.5),
 )
+#: BASELINE config 5 (96 kHz, six resolutions up to 32768): the reference defines no such list; ranges
+#: chosen per SURVEY.md section 7 and fed to the unmodified reference for the golden vectors
+CONFIG5_96K = (
+    ((20, 60), 32768, 1024, 1.5),
+    ((60, 200), 16384, 1024, 1.5),
+    ((200, 1000), 8192, 512, 1.2),
+    ((1000, 5000), 4096, 256, 1.0),
+    ((5000, 12000), 2048, 256, 1.2),
+    ((12000, 20000), 1024, 256, 1.5),
+)
 
 
 # --------------------------------------------------------------------------------------
@@ -422,6 +432,53 @@ def map_spectrum_to_bars(spectrum, bands, num_bars: int, comp: Optional[np.ndarr
 def magnitude_to_db(x) -> np.ndarray:
     """Consumers' dB conversion, panels/spectrogram_waterfall.py:85: 20 log10(max(x, 1e-10))."""
     return 20.0 * np.log10(np.maximum(np.asarray(x, dtype=np.float64), 1e-10))
+
+
+def magnitude_to_db_plus(x) -> np.ndarray:
+    """The plugin spectrogram panel's form, plugins/panels/spectrogram.py:72: 20 log10(x + 1e-10)."""
+    return 20.0 * np.log10(np.asarray(x, dtype=np.float64) + 1e-10)
+
+
+def waterfall_freq_indices(sample_rate: int, fft_size: int, min_freq: float = 20, max_freq: float = 20000):
+    """SpectrogramWaterfall._setup_frequency_mapping (panels/spectrogram_waterfall.py:55-69): first bin
+    >= min_freq, first bin >= max_freq (the last bin when max_freq lies beyond Nyquist)."""
+    bins = np.linspace(0, sample_rate / 2, fft_size // 2 + 1)
+    lo = int(np.argmax(bins >= min_freq))
+    hi = int(np.argmax(bins >= max_freq))
+    if hi == 0:
+        hi = len(bins) - 1
+    return lo, hi
+
+
+class OracleWaterfall:
+    """SpectrogramWaterfall.update + _normalize_spectrum (panels/spectrogram_waterfall.py:71-121), data side:
+    slice -> 20 log10(max(x, 1e-10)) -> (max, min) into a 100-entry history -> with auto gain the 95th
+    percentile of the last 20 maxima / 5th percentile of the last 20 minima -> (dB + gain - floor) /
+    (peak - floor) clipped to [0, 1] (zeros when the range is not positive).  float64 here; the
+    reference computes the same in float32."""
+
+    def __init__(self, sample_rate: int = 48000, fft_size: int = 2048):
+        self.freq_indices = waterfall_freq_indices(sample_rate, fft_size)
+        self.auto_gain = True
+        self.gain_adjustment = 0.0
+        self.peak_history = deque(maxlen=100)
+        self.current_peak = 0.0
+        self.current_floor = -80.0
+
+    def update(self, fft_data) -> Optional[np.ndarray]:
+        if fft_data is None or len(fft_data) == 0:
+            return None
+        lo, hi = self.freq_indices
+        db = magnitude_to_db(np.asarray(fft_data)[lo:hi])
+        self.peak_history.append((float(db.max()), float(db.min())))
+        if self.auto_gain:
+            recent = list(self.peak_history)[-20:]
+            self.current_peak = float(np.percentile([p[0] for p in recent], 95))
+            self.current_floor = float(np.percentile([p[1] for p in recent], 5))
+        rng = self.current_peak - self.current_floor
+        if rng > 0:
+            return np.clip((db + self.gain_adjustment - self.current_floor) / rng, 0.0, 1.0)
+        return np.zeros_like(db)
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,350 @@
+"""GPU parity tests added in round 2: BASELINE configs[4] (96 kHz, 8 channels, six resolutions up to 32768)
+as a verified configuration, the waterfall consumer, the bars kernel away from
+its default shape, the gate threshold, argument validation of the Python binding.
+
+Same bars as tests/test_gpu_parity.py: spectrum 0.01 dB, LUFS 0.01 LU, true peak 0.05 dBTP."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_spectrum_close
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_DB, TOL_LU, TOL_TP = 0.01, 0.01, 0.05
+HOP, W = 512, 2048
+
+
+def _names(plan):
+    return [n for n, _ in plan.kernel_times()]
+
+
+# ------------------------------------------------------------------ configs[4]: meters at 96 kHz
+def test_meters_96k_eight_channels_golden(golden):
+    """ProfessionalMetering(96000) on eight channels (professional_meters.py:48-72, 129-153, 231-299), fed in
+    the s16le wire format as one interleaved 7.1 stream -- through omega4_analyze_s16, through omega4_analyze
+    on the decoded planar rows, with the float32-state (default) and the float64-state K-weighting kernels."""
+    from omega4_b200.plan import AnalysisPlan, CONFIG5_96K
+    g = golden("meters_96k.npz")
+    x16 = g["x16"]                                                   # [8, n] planar int16
+    f = int(g["first_hop"])
+    plan = AnalysisPlan(96000, CONFIG5_96K, 512)
+    inter = np.ascontiguousarray(x16.T)[None, :, :]                  # [1 stream, n, 8 channels]
+    out = plan.analyze_s16_host(inter, want_combined=False, want_series=True)
+    worst = {}
+    for tag, o in (("s16", out),
+                   ("planar", plan.analyze_host(x16.astype(np.float32) / 32768.0, want_combined=False, want_series=True))):
+        dl = np.abs(o["lufs_inst"][:, f:] - g["lufs_inst"]).max()
+        dt = np.abs(o["tp_db"][:, f:] - g["tp_db"]).max()
+        dm = np.abs(o["meters"][:, f:].astype(np.float64) - g["meters"])
+        assert dl <= TOL_LU and dt <= TOL_TP, (tag, dl, dt)
+        assert dm[..., :4].max() <= TOL_LU and dm[..., 4].max() <= TOL_TP, (tag, dm.max(axis=(0, 1)))
+        assert np.all(o["meters"][:, :f] == [-100, -100, -100, 0, -100])
+        worst[tag] = (dl, dt)
+    assert np.array_equal(out["meters"], o["meters"])                # the decode is exact: bit-identical rows
+    # in practice far inside the gate, also with alpha four times smaller than at 48 kHz
+    assert worst["s16"][0] < 1e-4 and worst["s16"][1] < 1e-3, worst
+    assert np.all(out["lufs_inst"][1, 23:30] == -100.0)              # digital silence -> rms gate
+    assert np.all(out["meters"][4, :, 2] == -100.0)                  # a few LSB never pass the -70 gate
+    os.environ["OMEGA4_KW_F64"] = "1"
+    try:
+        o64 = plan.analyze_s16_host(inter, want_combined=False, want_series=True)
+    finally:
+        os.environ.pop("OMEGA4_KW_F64", None)
+    assert np.abs(o64["lufs_inst"][:, f:] - g["lufs_inst"]).max() < 1e-5
+    assert np.abs(o64["lufs_inst"][:, f:] - out["lufs_inst"][:, f:]).max() < 1e-4
+    plan.close()
+
+
+def test_meters_96k_through_the_shim(golden):
+    from omega4_b200.panels.professional_meters import ProfessionalMetering
+    g = golden("meters_96k.npz")
+    f = int(g["first_hop"])
+    for ch in (0, 2, 5):
+        x = g["x16"][ch].astype(np.float32) / 32768.0
+        m = ProfessionalMetering(96000)
+        np.testing.assert_allclose(m.k_weighting_filter["hp_a"], g["hp_a"], rtol=0, atol=3e-15)
+        for k in range(f, 40):
+            frame = x[(k + 1) * HOP - W:(k + 1) * HOP] * np.hanning(W)
+            d = m.calculate_lufs(frame)
+            want = g["meters"][ch, k - f]
+            got = np.array([d[key] for key in O.METER_KEYS])
+            assert np.abs(got[:4] - want[:4]).max() <= TOL_LU and abs(got[4] - want[4]) <= TOL_TP, (ch, k)
+            assert abs(m.calculate_true_peak(frame) - g["tp_db"][ch, k - f]) <= TOL_TP
+        fr40 = x[41 * HOP - W:41 * HOP] * np.hanning(W)
+        wk = m.apply_k_weighting(fr40)
+        ref = g[f"kweighted_c{ch}_h40"]
+        assert np.abs(wk - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------ configs[4]: six resolutions, adversarial stream
+def test_multires_96k_adversarial_stream_golden(golden):
+    """A click that crosses the 32768-sample window, digital silence and full-scale tones inside the 32768 /
+    16384 ranges: the default path (exact-windowing hop-block DFT on the tensor cores, 64 / 32 block positions
+    per bin) and the full FFT against the unmodified reference, per frame."""
+    from omega4_b200 import _native as N
+    from omega4_b200.plan import AnalysisPlan, CONFIG5_96K
+    g = golden("multires_96k_stress.npz")
+    x = g["x"]
+    f0 = int(g["combined_first"])
+    plan = AnalysisPlan(96000, CONFIG5_96K, 512)
+    got = {}
+    for tag, fl in (("default", 0), ("fft", N.FLAG_NO_BLOCKDFT)):
+        out = plan.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | fl)
+        names = _names(plan)
+        if tag == "default":
+            assert "blockdft_tc_gemm" in names and "blockdft_asm_32768" in names and "blockdft_asm_16384" in names, names
+            assert "multires_fft_32768" not in names and "multires_fft_16384" not in names
+        else:
+            assert "multires_fft_32768" in names and not any(n.startswith("blockdft") for n in names)
+        comb = out["combined"][0]
+        got[tag] = comb
+        low = comb[f0:, :32]
+        assert np.array_equal(low == 0, g["combined_low"] == 0), tag
+        # bins 1..5 come from the 32768 / 16384 transforms: the gate counts from the largest value they show
+        for k in range(low.shape[0]):
+            assert_spectrum_close(low[k, 1:6], g["combined_low"][k, 1:6], TOL_DB, label=f"{tag} hop {f0 + k} sparse bins")
+        for k in (75, 130, 149):
+            assert_spectrum_close(comb[k], g[f"combined_h{k}"], TOL_DB, label=f"{tag} hop {k}")
+        assert np.all(comb[:63, 1] == 0) and comb[63, 1] > 0           # 32768 / 512 - 1: first filled hop
+    scale = got["fft"].max(axis=1, keepdims=True) + 1e-20
+    assert (np.abs(got["fft"] - got["default"]) / scale).max() < 2e-5
+    # magnitudes of the two largest transforms (API-faithful output) at the probe hops
+    out = plan.analyze_host(x[None, :], want_meters=False, want_magnitudes=True)
+    for k in (75, 130, 149):
+        for r in (0, 1):
+            ref = g[f"mag_h{k}_r{r}"]
+            m = out["magnitudes"][r][0, k, :64]
+            assert np.abs(m - ref).max() <= 2e-6 * out["magnitudes"][r][0, k].max() + 1e-9, (k, r)
+    plan.close()
+
+
+@pytest.mark.parametrize("seed,mode", [(2, "tc"), (7, "tc"), (4, "fft")])
+def test_random_sections_96k_six_resolutions(seed, mode):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "random_stress.py"), str(seed), mode, "config5"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "random stress ok" in out.stdout
+
+
+def test_exact_windowing_edge_shapes_at_64_blocks(golden):
+    """Tiles with carried history and ragged lengths through the 64 / 32-position groups of the fused epilogue:
+    frames that straddle row tiles and calls that start inside a window must equal the one-shot result."""
+    import torch
+    from omega4_b200 import _native as N
+    from omega4_b200.batch.driver import StreamBatch
+    from omega4_b200.plan import AnalysisPlan, CONFIG5_96K
+    g = golden("multires_96k_stress.npz")
+    x = np.stack([g["x"], g["x"][::-1].copy()])
+    n_hops = x.shape[1] // HOP
+    plan = AnalysisPlan(96000, CONFIG5_96K, 512)
+    one = plan.analyze_host(x, want_meters=False)["combined"]
+    full = plan.analyze_host(x, want_meters=False, flags=N.FLAG_NO_BLOCKDFT)["combined"]
+    sb = StreamBatch(plan, 2, 67)
+    parts, done = [], 0
+    for n in (67, 1, 30, 52):
+        sb.tile_view(n).copy_(torch.from_numpy(x[:, done * HOP:(done + n) * HOP]))
+        comb = torch.empty((2, n, 512), device="cuda")
+        sb.push(n, combined=comb)
+        parts.append(comb.cpu().numpy())
+        done += n
+    assert done == n_hops
+    tiled = np.concatenate(parts, axis=1)
+    scale = full.max(axis=2, keepdims=True) + 1e-20
+    assert np.array_equal(tiled == 0, one == 0)
+    assert (np.abs(tiled - one) / scale).max() < 2e-6              # same kernels, different tile cuts: fp32 summation order only
+    assert (np.abs(one - full) / scale).max() < 2e-5
+    plan.close()
+
+
+# ------------------------------------------------------------------ section 8f rank 3: waterfall
+def test_waterfall_golden(golden):
+    """SpectrogramWaterfall.update (spectrogram_waterfall.py:71-121) frame by frame and as one batch, auto gain
+    on / off, with a gain adjustment; state carried between calls."""
+    from omega4_b200.panels.spectrogram_waterfall import SpectrogramWaterfall, spectrogram_db
+    g = golden("waterfall.npz")
+    spectra = g["spectra"]
+    freqs = np.fft.rfftfreq(2048, 1 / 48000)
+    for tag, auto, gain in (("auto", True, 0.0), ("fixed", False, 0.0), ("auto_gain3", True, 3.0)):
+        wf = SpectrogramWaterfall(48000, 2048)
+        assert wf.freq_indices == tuple(g["freq_indices"])
+        wf.auto_gain, wf.gain_adjustment = auto, gain
+        for k in range(len(spectra)):
+            row = wf.update(spectra[k], freqs)
+            assert abs(wf.current_peak - g[f"peak_{tag}"][k]) < 1e-3 and abs(wf.current_floor - g[f"floor_{tag}"][k]) < 1e-3, (tag, k)
+            assert np.abs(row - g[f"rows_{tag}"][k]).max() <= 2e-5, (tag, k)
+        assert len(wf.waterfall_data) == len(spectra) and len(wf.peak_history) == len(spectra)
+        # one batch == frame by frame; tiles with carried state == one batch
+        wb = SpectrogramWaterfall(48000, 2048)
+        wb.auto_gain, wb.gain_adjustment = auto, gain
+        rows, dbv = wb.update_batch(spectra, want_db=True)
+        assert np.array_equal(rows, np.stack(list(wf.waterfall_data)))
+        assert np.abs(dbv - 20 * np.log10(np.maximum(spectra[:, 1:854].astype(np.float64), 1e-10))).max() < TOL_DB
+        wt = SpectrogramWaterfall(48000, 2048)
+        wt.auto_gain, wt.gain_adjustment = auto, gain
+        tiles = np.concatenate([wt.update_batch(spectra[s:s + 7]) for s in range(0, len(spectra), 7)])
+        assert np.array_equal(tiles, rows)
+    assert SpectrogramWaterfall(96000, 4096).freq_indices == tuple(g["freq_indices_96k_4096"])
+    assert SpectrogramWaterfall(22050, 1024).freq_indices == tuple(g["freq_indices_22k_1024"])
+    wf = SpectrogramWaterfall()
+    assert wf.update(np.zeros(0), freqs) is None and wf.update(None, freqs) is None and len(wf.waterfall_data) == 0
+    # the plugin panel's dB form (plugins/panels/spectrogram.py:72)
+    assert np.abs(spectrogram_db(spectra[:8]) - g["plugin_db"]).max() < 1e-3
+    assert np.abs(spectrogram_db(spectra[3]) - g["plugin_db"][3]).max() < 1e-3
+
+
+def test_waterfall_device_batch_and_band_map_db_forms():
+    """Device-resident rows of many channels against the oracle; omega4_band_map's two dB forms."""
+    import torch
+    from omega4_b200 import _native as N
+    from omega4_b200.plan import band_map_host
+    rng = np.random.default_rng(3)
+    n_ch, n_rows, ln = 5, 33, 513
+    spec = (np.abs(rng.standard_normal((n_ch, n_rows, ln))) * 10 ** rng.uniform(-6, 1, (n_ch, n_rows, 1))).astype(np.float32)
+    spec[2, 10:14] = 0.0
+    lo, hi = O.waterfall_freq_indices(48000, 1024)
+    d_spec = torch.from_numpy(spec).cuda()
+    norm = torch.empty((n_ch, n_rows, hi - lo), device="cuda")
+    stat = torch.empty((n_ch, n_rows, 4), device="cuda")
+    state = torch.zeros((n_ch, N.WATERFALL_STATE), device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for a, b in ((0, 20), (20, 33)):                                   # two tiles, state carried on the device
+        sl = d_spec[:, a:b].contiguous()
+        no, so = torch.empty((n_ch, b - a, hi - lo), device="cuda"), torch.empty((n_ch, b - a, 4), device="cuda")
+        rc = N.lib().omega4_waterfall(0, s, N.MEM_DEVICE, sl.data_ptr(), n_ch, b - a, ln, lo, hi, 0, 1, 0.0, state.data_ptr(),
+                                      1 if a == 0 else 0, None, no.data_ptr(), so.data_ptr())
+        N.check(rc, "omega4_waterfall")
+        norm[:, a:b], stat[:, a:b] = no, so
+    torch.cuda.synchronize()
+    got, st = norm.cpu().numpy(), stat.cpu().numpy()
+    for ch in range(n_ch):
+        wf = O.OracleWaterfall(48000, 1024)
+        for k in range(n_rows):
+            want = wf.update(spec[ch, k])
+            assert abs(st[ch, k, 2] - wf.current_peak) < 1e-3 and abs(st[ch, k, 3] - wf.current_floor) < 1e-3
+            assert np.abs(got[ch, k] - want).max() <= 2e-5, (ch, k)
+    bands = O.mel_band_indices(48000, 1024, 64)
+    row = spec[0, :4]
+    lin = band_map_host(row, bands)
+    assert np.abs(band_map_host(row, bands, db=True) - O.magnitude_to_db(lin)).max() < 1e-3
+    assert np.abs(band_map_host(row, bands, db=2) - O.magnitude_to_db_plus(lin)).max() < 1e-3
+    with pytest.raises(N.Omega4CudaError):
+        N.check(N.lib().omega4_waterfall(0, None, N.MEM_HOST, spec.ctypes.data, 1, 1, ln, 5, 5, 0, 1, 0.0, None, 1, None,
+                                         spec.ctypes.data, None), "omega4_waterfall")
+
+
+# ------------------------------------------------------------------ bars kernel away from T = 512 / P98
+@pytest.mark.parametrize("T,q", [(40, 98.0), (50, 98.0), (64, 90.0), (100, 50.0), (300, 98.0), (300, 10.0), (512, 50.0), (1000, 90.0)])
+def test_bars_percentile_reference_for_any_shape(T, q):
+    """np.percentile(spectrum, q) normalisation for spectrum lengths and percentiles where a lane runs out of
+    candidates (the -1 pad used to win the unsigned-bit selection): band = sqrt(spectrum / P_q * 0.8) clamp."""
+    import ctypes as C
+    from omega4_b200 import _native as N
+    rng = np.random.default_rng(T * 7 + int(q))
+    spec = np.abs(rng.standard_normal((3, 9, T))).astype(np.float32)
+    spec[0, 0, :] = 0.0                                               # all-zero row: no scaling
+    spec[1, 2, 18:32] = 50.0                                          # the maxima inside one lane group
+    spec[2, 4, : T // 2] = 0.0                                        # half of the row exactly zero
+    bands = np.ascontiguousarray(np.stack([np.arange(T), np.arange(T) + 1], axis=1).astype(np.int32))   # identity bands
+    d = N.BarsDesc()
+    d.spectrum_len, d.n_bars = T, T
+    d.bands = bands.ctypes.data_as(C.POINTER(C.c_int))
+    d.gain = None
+    d.smooth = None
+    d.percentile, d.scale, d.normalize_max = q, 0.8, 0
+    h = N.lib().omega4_bars_create(C.byref(d), 0)
+    assert h, N.last_error()
+    out = np.empty((3, 9, T), np.float32)
+    N.check(N.lib().omega4_bars_run(h, None, N.MEM_HOST, spec.ctypes.data, 3, 9, None, 1, out.ctypes.data, None), "omega4_bars_run")
+    N.lib().omega4_bars_destroy(h)
+    for c in range(3):
+        for k in range(9):
+            row = spec[c, k]
+            x = row
+            if row.max() > 0:
+                ref = np.percentile(row, q)
+                if ref > 0:
+                    x = row / ref * 0.8
+            want = np.clip(np.sqrt(x), 0, 1)
+            assert np.abs(out[c, k] - want).max() <= 1e-5, (T, q, c, k)
+
+
+def test_bars_state_copy_with_many_segments():
+    """Carried smoothing state with more than one segment per channel: segment 0 reads a private copy of the
+    state the last segment overwrites."""
+    import torch
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    rng = np.random.default_rng(12)
+    spec = np.abs(rng.standard_normal((3, 1100, 512))).astype(np.float32)
+    post = SpectrumPostProcessor(512)
+    post._ensure()
+    ref = post.process_host(spec)
+    d = torch.from_numpy(spec).cuda()
+    state = torch.zeros((3, 1 + post.n_valid), device="cuda")
+    a = torch.empty((3, 550, post.n_valid), device="cuda")
+    b = torch.empty((3, 550, post.n_valid), device="cuda")
+    post.process_device(d[:, :550].contiguous(), a, state=state, fresh=True)
+    post.process_device(d[:, 550:].contiguous(), b, state=state, fresh=False)
+    torch.cuda.synchronize()
+    got = torch.cat([a, b], dim=1).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-6
+    post.close()
+
+
+# ------------------------------------------------------------------ gate threshold, binding validation
+def test_gate_threshold_is_honoured(plan48):
+    from omega4_b200 import _native as N
+    rng = np.random.default_rng(4)
+    li = rng.uniform(-90, -10, 300)
+    tp = rng.uniform(-60, 0, 300)
+    for gate in (-70.0, -40.0):
+        plan48.set_gate_threshold(gate)
+        got = plan48.meter_stats_host(li, tp, fresh=True)[0]
+        st = O.OracleMeterStats()
+        st.gate = gate
+        want = np.array([[st.push(a, b)[k] for k in O.METER_KEYS] for a, b in zip(li, tp)])
+        assert np.abs(got - want).max() <= 1e-4, gate
+    plan48.set_gate_threshold(-70.0)
+    from omega4_b200.panels.professional_meters import ProfessionalMetering
+    m = ProfessionalMetering(48000)
+    m.gate_threshold = -5.0                                           # everything gated out
+    t = np.arange(W) / 48000.0
+    d = m.calculate_lufs(0.3 * np.sin(2 * np.pi * 1000 * t) * np.hanning(W))
+    assert d["integrated"] == -100.0 and d["range"] == 0.0 and d["momentary"] > -40
+
+
+def test_binding_rejects_bad_buffers(plan48):
+    import torch
+    from omega4_b200 import _native as N
+    x = torch.zeros((2, 20 * HOP), device="cuda")
+    comb = torch.empty((2, 20, 512), device="cuda")
+    with pytest.raises(N.Omega4CudaError):                            # one entry per resolution
+        plan48.analyze_device(x, 20, combined=comb, magnitudes=[None, None])
+    with pytest.raises(N.Omega4CudaError):                            # wrong dtype
+        plan48.analyze_device(x, 20, combined=comb.double())
+    with pytest.raises(N.Omega4CudaError):                            # too small
+        plan48.analyze_device(x, 20, combined=comb[:, :10].contiguous())
+    with pytest.raises(N.Omega4CudaError):                            # non-contiguous
+        plan48.analyze_device(x, 20, combined=torch.empty((2, 20, 1024), device="cuda")[:, :, ::2])
+    with pytest.raises(N.Omega4CudaError):                            # float32 state
+        plan48.analyze_device(x, 20, combined=comb, meters=torch.empty((2, 20, 5), device="cuda"),
+                              meter_state=torch.zeros((2, N.METER_STATE_DOUBLES), device="cuda"))
+    with pytest.raises(N.Omega4CudaError):
+        plan48.analyze_device(x, 21, combined=comb)                   # rows shorter than n_hops * hop
+    # a state vector with garbage counts must not index out of range (clamped in the kernel)
+    st = np.full((1, N.METER_STATE_DOUBLES), 1e9)
+    out = plan48.meter_stats_host(np.full(10, -20.0), np.full(10, -3.0), state=st, fresh=False)
+    assert out.shape == (1, 10, 5)
+
+
+@pytest.fixture(scope="module")
+def plan48():
+    from omega4_b200.plan import AnalysisPlan, BASELINE_CONFIGS
+    p = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
+    yield p
+    p.close()

@@ -352,3 +352,59 @@ def test_bass_zoom_bars_match_reference(golden):
     for fr, want in zip(g["frames"], g["bars"]):
         bars = O.bass_bars_step(fr.astype(np.float64), bars, ranges, groups)
         np.testing.assert_allclose(bars, want, rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------ round 2 fixtures (oracle/gen_golden_r2.py)
+def test_meters_96k_eight_channels(golden):
+    """BASELINE configs[4] shape for the meters: ProfessionalMetering(96000) on 8 channels of s16le audio."""
+    g = golden("meters_96k.npz")
+    assert int(g["sample_rate"]) == 96000
+    c = O.k_weighting_coeffs(96000)
+    for k in ("hp_b", "hp_a", "shelf_b", "shelf_a"):
+        np.testing.assert_allclose(c[k], g[k], rtol=0, atol=3e-15)
+    x = g["x16"].astype(np.float32) / 32768.0                       # capture.py:574
+    assert x.shape[0] == 8
+    for ch in range(8):
+        first, frames = O.meter_frames(x[ch], HOP, W)
+        assert first == int(g["first_hop"])
+        inst = O.lufs_instantaneous(frames, c)
+        tp = O.true_peak_db(frames)
+        np.testing.assert_allclose(inst, g["lufs_inst"][ch], rtol=0, atol=2e-9)
+        np.testing.assert_allclose(tp, g["tp_db"][ch], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(O.apply_k_weighting(frames[40 - first][None], c)[0], g[f"kweighted_c{ch}_h40"],
+                                   rtol=0, atol=1e-12)
+        full = O.analyze_channel(x[ch], 96000, O.BASELINE_CONFIGS)
+        np.testing.assert_allclose(full["meters"][first:], g["meters"][ch], rtol=0, atol=2e-9)
+    assert np.all(g["lufs_inst"][1][23 - 3:30 - 3] == -100.0)       # digital silence -> rms gate
+    assert g["tp_db"][2].max() > 0.0                                # the hot channel crosses 0 dBTP
+    assert g["meters"][4][:, 2].max() == -100.0                     # a few LSB: never above the -70 gate
+
+
+def test_waterfall_matches_reference(golden):
+    g = golden("waterfall.npz")
+    assert O.waterfall_freq_indices(48000, 2048) == tuple(g["freq_indices"])
+    assert O.waterfall_freq_indices(96000, 4096) == tuple(g["freq_indices_96k_4096"])
+    assert O.waterfall_freq_indices(22050, 1024) == tuple(g["freq_indices_22k_1024"])
+    for tag, auto, gain in (("auto", True, 0.0), ("fixed", False, 0.0), ("auto_gain3", True, 3.0)):
+        wf = O.OracleWaterfall(48000, 2048)
+        wf.auto_gain, wf.gain_adjustment = auto, gain
+        for k, spec in enumerate(g["spectra"]):
+            row = wf.update(spec)
+            # the reference works in float32: dB values up to 200 in magnitude carry ~1.5e-5 of rounding
+            assert abs(wf.current_peak - g[f"peak_{tag}"][k]) < 1e-4 and abs(wf.current_floor - g[f"floor_{tag}"][k]) < 1e-4
+            np.testing.assert_allclose(row, g[f"rows_{tag}"][k], rtol=0, atol=2e-6)
+    assert O.OracleWaterfall().update(np.zeros(0)) is None
+    np.testing.assert_allclose(O.magnitude_to_db_plus(g["spectra"][:8]), g["plugin_db"], rtol=0, atol=2e-5)
+
+
+def test_multires_96k_adversarial_stream(golden):
+    """Six resolutions up to 32768 at 96 kHz on a click / silence / full-scale-tone stream."""
+    g = golden("multires_96k_stress.npz")
+    cfgs = [(c[0], c[1], c[2], c[3]) for c in O.CONFIG5_96K]
+    comb, present, kept = _run_oracle_multires(g["x"], 96000, cfgs, 512, (75, 130, 149))
+    f0 = int(g["combined_first"])
+    np.testing.assert_allclose(comb[f0:, :32], g["combined_low"], rtol=3e-6, atol=1e-9)
+    for k in (75, 130, 149):
+        np.testing.assert_allclose(comb[k], g[f"combined_h{k}"], rtol=3e-6, atol=1e-9)
+        for i in (0, 1):
+            np.testing.assert_allclose(kept[(k, i)][:64], g[f"mag_h{k}_r{i}"], rtol=3e-6, atol=1e-7)

@@ -19,19 +19,21 @@ EXT = W + 2*PAD
 OFF = [0, 17, 33, 49, 65]
 
 def consts(b, a):
+    """Kw32Sec as build_kw32 derives it (csrc/omega4_cuda.cu): everything in float64, then rounded once."""
     b0 = b[0]; a1, a2 = a[1], a[2]
     alpha = 1.0 + a1 + a2; beta = 1.0 - a2
-    M = np.array([[1 - alpha, a2], [-alpha, a2]])
+    bb = -b0 * beta; gamma = alpha / bb
+    M = np.array([[1 - alpha, bb * a2], [-gamma, a2]])
     def P(k): return np.linalg.matrix_power(M, k)
-    c = dict(b0=f32(b0), alpha=f32(alpha), a2=f32(a2), bb=f32(-b0 * beta), ab=f32(-b0 * alpha))
+    c = dict(b0=f32(b0), a2=f32(a2), gamma=f32(gamma), bb=f32(bb))
     c['phi'] = [P(65 * 2**j).astype(f32) for j in range(5)]
     c['c16'] = P(16).astype(f32); c['c17'] = P(17).astype(f32)
     c['g'] = np.stack([P(i + 1)[0] for i in range(17)]).astype(f32)
     return c
 
 def sweep_pass(r, c, backward):
-    """y = b0 x + z;  z[n] = z[n-1] + d[n];  d[n] = a2 d[n-1] - alpha z[n-1] + u[n],
-    u[n] = -b0 (beta (x[n-1]-x[n-2]) + alpha x[n-1]).  Zero-state sub-chunk sweeps + scan + correction, float32."""
+    """kw32_pass: y = b0 x + z;  delta = a2 delta' + (x' - x'') - gamma y';  z = z' + bb delta.
+    Zero-state sub-chunk sweeps + scan of the (z, delta) chunk states + homogeneous correction, float32."""
     F = r.shape[0]
     if backward:
         r = r[:, ::-1, ::-1]
@@ -40,21 +42,21 @@ def sweep_pass(r, c, backward):
     xa[:, 0] = r[:, 0, 0]; xb[:, 0] = r[:, 0, 0]
     offs = OFF if not backward else [0, 16, 32, 48, 65]
     rin = r.copy()
-    zs = np.empty_like(rin)
+    ys = np.empty_like(rin)
     esub = []
     for m in range(4):
         lo, hi = offs[m], offs[m + 1]
-        if m == 0: pa, pb = xa, xb
-        else: pa, pb = rin[:, :, lo - 1], rin[:, :, lo - 2]
-        z1 = np.zeros((F, 32), f32); d1 = np.zeros((F, 32), f32)
+        if m == 0: pa, dx = xa, xa - xb
+        else: pa, dx = rin[:, :, lo - 1], rin[:, :, lo - 1] - rin[:, :, lo - 2]
+        z1 = np.zeros((F, 32), f32); d1 = np.zeros((F, 32), f32); y1 = c['b0'] * pa
         for i in range(lo, hi):
             x = rin[:, :, i]
-            u = c['bb'] * (pa - pb) + c['ab'] * pa
-            t = c['a2'] * d1 + u
-            d = t - c['alpha'] * z1
-            z = z1 + d
-            pb = pa; pa = x; z1 = z; d1 = d
-            zs[:, :, i] = z
+            t = c['a2'] * d1 + dx
+            d = t - c['gamma'] * y1
+            z = z1 + c['bb'] * d
+            y = c['b0'] * x + z
+            dx = x - pa; pa = x; z1 = z; d1 = d; y1 = y
+            ys[:, :, i] = y
         esub.append(np.stack((z1, d1), -1))
     v = esub[0]
     for m in range(1, 4):
@@ -74,8 +76,7 @@ def sweep_pass(r, c, backward):
             cm = c['c17'] if (offs[m] - offs[m - 1]) == 17 else c['c16']
             sin = (sin @ cm.T).astype(f32) + esub[m - 1]
         for n, i in enumerate(range(lo, hi)):
-            zt = zs[:, :, i] + (c['g'][n, 0] * sin[:, :, 0] + c['g'][n, 1] * sin[:, :, 1])
-            r[:, :, i] = c['b0'] * rin[:, :, i] + zt
+            r[:, :, i] = ys[:, :, i] + (c['g'][n, 0] * sin[:, :, 0] + c['g'][n, 1] * sin[:, :, 1])
 
 def filtfilt32(x, c):
     F = x.shape[0]
@@ -93,8 +94,8 @@ def filtfilt32(x, c):
 SR = int(sys.argv[1]) if __name__ == '__main__' and len(sys.argv) > 1 else 48000
 
 
-def lufs32(frames64):
-    co = O.k_weighting_coeffs(SR)
+def lufs32(frames64, sample_rate=None):
+    co = O.k_weighting_coeffs(sample_rate or SR)
     c1 = consts(co['hp_b'], co['hp_a']); c2 = consts(co['shelf_b'], co['shelf_a'])
     x = frames64.astype(f32)
     f = filtfilt32(x, c1)
