@@ -338,6 +338,54 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// ------------------------------------------------------------------------------------------
+// application post-processing object (omega4_bars_*); also used fused behind the combine by omega4_analyze_io
+// ------------------------------------------------------------------------------------------
+struct omega4_bars {
+    int device = 0, T = 0, n_valid = 0, p_lo = 0, normalize_max = 0;
+    float p_frac = 0.f, scale = 0.8f;
+    int* bands = nullptr; float* gain = nullptr; float* sf = nullptr; float* sfc = nullptr;
+    DevBuf h_spec, h_out, h_peak, h_state, state_in;
+};
+
+// spectrum [n_ch][n_hops][T] (device) -> band values (+ unsmoothed peaks) on stream s; state (device) carries the
+// smoothing recurrence between calls.  state_copy: scratch for the private copy segment 0 reads when a channel is cut
+// into several segments (the last segment overwrites the state in the same launch).
+static int bars_launch(omega4_bars* b, cudaStream_t s, const float* spec, int n_ch, int n_hops, float* state, int fresh,
+                       float* band_values, float* peak_values, DevBuf* state_copy) {
+    BarsArgs a;
+    memset(&a, 0, sizeof a);
+    a.T = b->T; a.n_ch = n_ch; a.n_hops = n_hops; a.n_valid = b->n_valid; a.bands = b->bands; a.gain = b->gain;
+    a.sf = b->sf; a.sfc = b->sfc; a.p_lo = b->p_lo; a.p_frac = b->p_frac; a.scale = b->scale;
+    a.normalize_max = b->normalize_max; a.fresh = (fresh || !state) ? 1 : 0;
+    a.spec = spec; a.bars_out = band_values; a.peaks_out = peak_values; a.state = state;
+    const size_t st_bytes = (size_t)n_ch * (1 + b->n_valid) * sizeof(float);
+    const size_t smem = bars_smem_bytes(b->T, b->n_valid);
+    if (smem > 200 * 1024) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel");
+    if (b->T > 32 * BARS_MAXV) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel (max 1024 bins)");
+    if (b->T <= 512) CK(cudaFuncSetAttribute(bars_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(bars_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.seg = n_ch >= 1024 ? 4 * BARS_SEG : BARS_SEG;              // fewer warm-up replays when channels alone fill the GPU
+    const long long grid = (long long)n_ch * ((n_hops + a.seg - 1) / a.seg);
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "bars grid too large");
+    if (a.state && !a.fresh && n_hops > a.seg) {
+        int rc = state_copy->ensure(st_bytes); if (rc) return rc;
+        CK(cudaMemcpyAsync(state_copy->p, a.state, st_bytes, cudaMemcpyDeviceToDevice, s));
+        a.state_in = (const float*)state_copy->p;
+    }
+    if (b->T <= 512) bars_kernel<16><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
+    else bars_kernel<32><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+// what omega4_analyze_io adds to a plain analyze call
+struct BarsReq {
+    omega4_bars* b = nullptr;
+    float* band_values = nullptr; float* peak_values = nullptr; float* state = nullptr;
+    int fresh = 1;
+};
+
 struct KernelTime { char name[32]; cudaEvent_t e0, e1; };
 
 // side stream + fork/join events of one caller stream (plan-level for device calls, one per host slot)
@@ -380,13 +428,14 @@ struct omega4_plan {
     SparseSet set_cc;             // fp32 CUDA-core GEMM: up to 128 columns
     SparseSet set_tc;             // 3xTF32 tcgen05 GEMM: up to 512 columns
     bool tensor_default = true;   // OMEGA4_TENSOR=0 makes the CUDA-core GEMM the default
-    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32;
+    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32, scratch_comb, scratch_bstate;
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
     // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
     // that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
     struct Slot {
         cudaStream_t s = nullptr;
         DevBuf in, in16, comb, met, lufs, tp, state, q, mag[OMEGA4_MAX_RES];
+        DevBuf bars, peaks, bstate, bstate_copy;          // omega4_analyze_io: fused application post-processing
         SideCtx sc;
     };
 #ifndef OMEGA4_HOST_SLOTS
@@ -810,9 +859,12 @@ extern "C" omega4_plan* omega4_plan_create(const omega4_plan_desc* desc, int dev
     return p;
 }
 
+static void stream_ctx_release(omega4_plan* p);
+
 extern "C" void omega4_plan_destroy(omega4_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    stream_ctx_release(p);
     for (int r = 0; r < OMEGA4_MAX_RES; ++r) {
         ResInfo& ri = p->res[r];
         cudaFree(ri.window); cudaFree(ri.binw); cudaFree(ri.tb_idx); cudaFree(ri.tb_lo); cudaFree(ri.tb_frac);
@@ -821,12 +873,14 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
     cudaFree(p->hann64); cudaFree(p->hann32); cudaFree(p->tp_rot);
     p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
+    p->scratch_comb.release(); p->scratch_bstate.release();
     p->set_cc.release(); p->set_tc.release();
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
     p->h_f64a.release(); p->h_f64b.release(); p->h_f64c.release();
     for (auto& sl : p->slots) {
         sl.in.release(); sl.comb.release(); sl.met.release(); sl.lufs.release(); sl.tp.release(); sl.state.release();
         sl.q.release(); sl.in16.release(); sl.sc.release();
+        sl.bars.release(); sl.peaks.release(); sl.bstate.release(); sl.bstate_copy.release();
         for (auto& m : sl.mag) m.release();
         if (sl.s) cudaStreamDestroy(sl.s);
     }
@@ -1173,8 +1227,14 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
 static int analyze_any(omega4_plan* p, void* stream, int mem, const float* samples, const int16_t* s16, int il,
                        long long ch_stride, int n_ch, int n_hops, int hist_samples, float* combined,
                        float* const* magnitudes, float* meters, double* lufs_inst, double* tp_db,
-                       double* meter_state, int flags) {
+                       double* meter_state, int flags, const BarsReq* br = nullptr) {
     if (!p) return fail(OMEGA4_ERR_INVALID, "plan is NULL");
+    if (br && !br->b) br = nullptr;
+    if (br) {
+        if (!br->band_values) return fail(OMEGA4_ERR_INVALID, "band_values is NULL");
+        if (br->b->device != p->device || br->b->T != p->T)
+            return fail(OMEGA4_ERR_INVALID, "the bars object must live on the plan's device and take spectra of target_bins values");
+    }
     if ((!samples && !s16) || n_ch < 0 || n_hops < 0 || hist_samples < 0) return fail(OMEGA4_ERR_INVALID, "bad samples / sizes");
     if (s16 && (il < 1 || il > 64 || n_ch % il != 0)) return fail(OMEGA4_ERR_INVALID, "bad interleave");
     if (n_ch == 0 || n_hops == 0) return OMEGA4_OK;
@@ -1191,11 +1251,18 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
             rc = launch_s16_convert(s16 - (long long)hist_samples * il, ch_stride, il, n_ch / il, len,
                                     d_in + (hist_al - hist_samples), dstride, s);
             if (rc) return rc;
-            return analyze_device(p, s, d_in + hist_al, dstride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
-                                  lufs_inst, tp_db, meter_state, flags, &p->scratch_q, &p->sc);
+            samples = d_in + hist_al; ch_stride = dstride;
         }
-        return analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, combined, magnitudes, meters,
-                              lufs_inst, tp_db, meter_state, flags, &p->scratch_q, &p->sc);
+        float* d_comb = combined;
+        if (br && !d_comb) {
+            int rc = p->scratch_comb.ensure((size_t)n_ch * n_hops * p->T * sizeof(float)); if (rc) return rc;
+            d_comb = (float*)p->scratch_comb.p;
+        }
+        int rc = analyze_device(p, s, samples, ch_stride, n_ch, n_hops, hist_samples, d_comb, magnitudes, meters,
+                                lufs_inst, tp_db, meter_state, flags, &p->scratch_q, &p->sc);
+        if (rc || !br) return rc;
+        p->launches++;
+        return bars_launch(br->b, s, d_comb, n_ch, n_hops, br->state, br->fresh, br->band_values, br->peak_values, &p->scratch_bstate);
     }
     if (mem != OMEGA4_MEM_HOST) return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
 
@@ -1206,18 +1273,19 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
     const long long new_len = (long long)n_hops * p->hop;
     const long long dstride = (hist_al + new_len + 3) / 4 * 4;
     size_t per_ch = (size_t)dstride * sizeof(float) + (size_t)n_hops * 2 * sizeof(double) + ST_STATE * sizeof(double);
-    if (combined) per_ch += (size_t)n_hops * p->T * sizeof(float);
+    if (combined || br) per_ch += (size_t)n_hops * p->T * sizeof(float);
+    if (br) per_ch += (size_t)n_hops * br->b->n_valid * sizeof(float) * (br->peak_values ? 2 : 1);
     {
         const bool tensor_sel = p->set_tc.n > 0 && (p->tensor_default ? !(flags & OMEGA4_FLAG_NO_TENSOR) : (flags & OMEGA4_FLAG_TENSOR) != 0);
         const SparseSet& sset = tensor_sel ? p->set_tc : p->set_cc;
-        if (combined && sset.n > 0 && !(flags & OMEGA4_FLAG_NO_BLOCKDFT))
+        if ((combined || br) && sset.n > 0 && !(flags & OMEGA4_FLAG_NO_BLOCKDFT))
             per_ch += (tensor_sel && sset.fusable) ? (size_t)(n_hops + 64) * sset.nkx * sizeof(float2)
                                                    : (size_t)(n_hops + 64) * sset.qs * sizeof(float);
     }
     if (meters) per_ch += (size_t)n_hops * 5 * sizeof(float);
     bool want_mag[OMEGA4_MAX_RES] = {false};
     for (int r = 0; r < p->n_res; ++r) {
-        want_mag[r] = (magnitudes && magnitudes[r]) || (combined && !p->disjoint);
+        want_mag[r] = (magnitudes && magnitudes[r]) || ((combined || br) && !p->disjoint);
         if (want_mag[r]) per_ch += (size_t)n_hops * p->res[r].bins * sizeof(float);
     }
     if (s16) per_ch += (size_t)(hist + new_len) * sizeof(int16_t);
@@ -1253,7 +1321,18 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
         float* d_comb = nullptr; float* d_met = nullptr; double* d_state = nullptr;
         double* d_lufs = nullptr; double* d_tp = nullptr;
         float* d_mag[OMEGA4_MAX_RES] = {nullptr};
-        if (combined) { rc = sl.comb.ensure(rows * p->T * sizeof(float)); if (rc) return rc; d_comb = (float*)sl.comb.p; }
+        if (combined || br) { rc = sl.comb.ensure(rows * p->T * sizeof(float)); if (rc) return rc; d_comb = (float*)sl.comb.p; }
+        float* d_bars = nullptr; float* d_peaks = nullptr; float* d_bstate = nullptr;
+        const size_t bst_row = br ? (size_t)(1 + br->b->n_valid) : 0;
+        if (br) {
+            rc = sl.bars.ensure(rows * br->b->n_valid * sizeof(float)); if (rc) return rc; d_bars = (float*)sl.bars.p;
+            if (br->peak_values) { rc = sl.peaks.ensure(rows * br->b->n_valid * sizeof(float)); if (rc) return rc; d_peaks = (float*)sl.peaks.p; }
+            if (br->state) {
+                rc = sl.bstate.ensure((size_t)nc * bst_row * sizeof(float)); if (rc) return rc; d_bstate = (float*)sl.bstate.p;
+                if (!br->fresh)
+                    CK(cudaMemcpyAsync(d_bstate, br->state + (size_t)c0 * bst_row, (size_t)nc * bst_row * sizeof(float), cudaMemcpyHostToDevice, sl.s));
+            }
+        }
         if (meters) { rc = sl.met.ensure(rows * 5 * sizeof(float)); if (rc) return rc; d_met = (float*)sl.met.p; }
         if (want_series) {
             rc = sl.lufs.ensure(rows * sizeof(double)); if (rc) return rc; d_lufs = (double*)sl.lufs.p;
@@ -1277,6 +1356,15 @@ static int analyze_any(omega4_plan* p, void* stream, int mem, const float* sampl
                             d_met, d_lufs, d_tp, d_state, fl, &sl.q, &sl.sc);
         if (rc) return rc;
         const size_t r0 = (size_t)c0 * n_hops;
+        if (br) {
+            p->launches++;
+            rc = bars_launch(br->b, sl.s, d_comb, nc, n_hops, d_bstate, br->fresh, d_bars, d_peaks, &sl.bstate_copy);
+            if (rc) return rc;
+            const size_t nv = (size_t)br->b->n_valid;
+            CK(cudaMemcpyAsync(br->band_values + r0 * nv, d_bars, rows * nv * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
+            if (br->peak_values) CK(cudaMemcpyAsync(br->peak_values + r0 * nv, d_peaks, rows * nv * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
+            if (br->state) CK(cudaMemcpyAsync(br->state + (size_t)c0 * bst_row, d_bstate, (size_t)nc * bst_row * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
+        }
         if (combined) CK(cudaMemcpyAsync(combined + r0 * p->T, d_comb, rows * p->T * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
         if (meters) CK(cudaMemcpyAsync(meters + r0 * 5, d_met, rows * 5 * sizeof(float), cudaMemcpyDeviceToHost, sl.s));
         if (lufs_inst) CK(cudaMemcpyAsync(lufs_inst + r0, d_lufs, rows * sizeof(double), cudaMemcpyDeviceToHost, sl.s));
@@ -1311,6 +1399,166 @@ extern "C" int omega4_analyze_s16(omega4_plan* p, void* stream, int mem, const i
     if (mem == OMEGA4_MEM_DEVICE && ((uintptr_t)frames & 1)) return fail(OMEGA4_ERR_INVALID, "frames must be 2-byte aligned");
     return analyze_any(p, stream, mem, nullptr, frames, n_interleaved, stream_stride, n_streams * n_interleaved, n_hops,
                        hist_frames, combined, magnitudes, meters, lufs_inst, tp_db, meter_state, flags);
+}
+
+extern "C" int omega4_analyze_io(omega4_plan* p, void* stream, int mem, const omega4_io* io) {
+    if (!io) return fail(OMEGA4_ERR_INVALID, "io is NULL");
+    if ((io->samples != nullptr) == (io->frames_s16 != nullptr))
+        return fail(OMEGA4_ERR_INVALID, "exactly one of samples / frames_s16 must be given");
+    BarsReq br;
+    br.b = io->bars; br.band_values = io->band_values; br.peak_values = io->peak_values; br.state = io->bars_state;
+    br.fresh = (!io->bars_state || (io->flags & OMEGA4_FLAG_FRESH_BARS)) ? 1 : 0;
+    if (io->frames_s16) {
+        if (io->n_interleaved < 1 || io->n_ch % io->n_interleaved != 0) return fail(OMEGA4_ERR_INVALID, "bad interleave");
+        if (mem == OMEGA4_MEM_DEVICE && ((uintptr_t)io->frames_s16 & 1)) return fail(OMEGA4_ERR_INVALID, "frames must be 2-byte aligned");
+        return analyze_any(p, stream, mem, nullptr, io->frames_s16, io->n_interleaved, io->stride, io->n_ch, io->n_hops, io->hist,
+                           io->combined, io->magnitudes, io->meters, io->lufs_inst, io->tp_db, io->meter_state, io->flags, &br);
+    }
+    return analyze_any(p, stream, mem, io->samples, nullptr, 1, io->stride, io->n_ch, io->n_hops, io->hist, io->combined,
+                       io->magnitudes, io->meters, io->lufs_inst, io->tp_db, io->meter_state, io->flags, &br);
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming entry points: one round trip per application frame
+// ------------------------------------------------------------------------------------------
+struct StreamCtx {
+    cudaStream_t s = nullptr;
+    float* h_in = nullptr; float* h_out = nullptr;       // pinned staging
+    size_t h_in_cap = 0, h_out_cap = 0;
+    DevBuf d_in, d_out;
+    double* h64 = nullptr; size_t h64_cap = 0;            // pinned staging of the meter update
+    DevBuf d64;
+    int ensure(size_t in_bytes, size_t out_bytes) {
+        if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        if (in_bytes > h_in_cap) { if (h_in) cudaFreeHost(h_in); h_in = nullptr; h_in_cap = 0; CK(cudaMallocHost(&h_in, in_bytes)); h_in_cap = in_bytes; }
+        if (out_bytes > h_out_cap) { if (h_out) cudaFreeHost(h_out); h_out = nullptr; h_out_cap = 0; CK(cudaMallocHost(&h_out, out_bytes)); h_out_cap = out_bytes; }
+        int rc = d_in.ensure(in_bytes); if (rc) return rc;
+        return d_out.ensure(out_bytes);
+    }
+    int ensure64(size_t bytes) {
+        if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        if (bytes > h64_cap) { if (h64) cudaFreeHost(h64); h64 = nullptr; h64_cap = 0; CK(cudaMallocHost(&h64, bytes)); h64_cap = bytes; }
+        return d64.ensure(bytes);
+    }
+    void release() {
+        if (h_in) cudaFreeHost(h_in); if (h_out) cudaFreeHost(h_out); if (h64) cudaFreeHost(h64);
+        d_in.release(); d_out.release(); d64.release();
+        if (s) cudaStreamDestroy(s);
+        h_in = h_out = nullptr; h64 = nullptr; s = nullptr; h_in_cap = h_out_cap = h64_cap = 0;
+    }
+};
+static std::mutex g_sc_mu;
+static std::map<omega4_plan*, StreamCtx> g_stream_ctx;
+static StreamCtx* stream_ctx(omega4_plan* p) { std::lock_guard<std::mutex> lk(g_sc_mu); return &g_stream_ctx[p]; }
+static void stream_ctx_release(omega4_plan* p) {
+    std::lock_guard<std::mutex> lk(g_sc_mu);
+    auto it = g_stream_ctx.find(p);
+    if (it != g_stream_ctx.end()) { it->second.release(); g_stream_ctx.erase(it); }
+}
+
+extern "C" int omega4_stream_hop(omega4_plan* p, const float* const* frames, float* const* magnitudes, float* combined) {
+    if (!p || !frames || !magnitudes) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(p->device));
+    size_t in_off[OMEGA4_MAX_RES], out_off[OMEGA4_MAX_RES], in_tot = 0, out_tot = 0;
+    int n_ready = 0;
+    for (int r = 0; r < p->n_res; ++r) {
+        in_off[r] = in_tot; out_off[r] = out_tot;
+        if (frames[r]) {
+            if (!magnitudes[r]) return fail(OMEGA4_ERR_INVALID, "a ready resolution needs a magnitude buffer");
+            in_tot += (size_t)p->res[r].n; out_tot += ((size_t)p->res[r].bins + 3) / 4 * 4; ++n_ready;
+        }
+    }
+    const size_t comb_off = out_tot;
+    if (combined) out_tot += (size_t)p->T;
+    if (n_ready == 0) {
+        if (combined) memset(combined, 0, (size_t)p->T * sizeof(float));
+        return OMEGA4_OK;
+    }
+    StreamCtx* c = stream_ctx(p);
+    int rc = c->ensure(in_tot * sizeof(float), out_tot * sizeof(float)); if (rc) return rc;
+    for (int r = 0; r < p->n_res; ++r)
+        if (frames[r]) memcpy(c->h_in + in_off[r], frames[r], (size_t)p->res[r].n * sizeof(float));
+    CK(cudaMemcpyAsync(c->d_in.p, c->h_in, in_tot * sizeof(float), cudaMemcpyHostToDevice, c->s));
+    CombineArgs cb;
+    memset(&cb, 0, sizeof cb);
+    for (int r = 0; r < p->n_res; ++r) {
+        cb.bins[r] = p->res[r].bins; cb.first_frame[r] = 0; cb.weight[r] = p->res[r].weight;
+        if (!frames[r]) continue;
+        const ResInfo& ri = p->res[r];
+        MultiresArgs a;
+        memset(&a, 0, sizeof a);
+        a.x = (const float*)c->d_in.p + in_off[r]; a.ch_stride = 0; a.frame_stride = ri.n; a.frame_off0 = 0;
+        a.n_ch = 1; a.n_frames = 1; a.first_frame = 0; a.rounds = 1;
+        a.window = ri.window; a.binw = ri.binw; a.twM = ri.tw.twM; a.twN = ri.tw.twN;
+        a.mag_out = (float*)c->d_out.p + out_off[r];
+        p->launches++;
+        rc = launch_multires(ri.log2m, a, c->s);
+        if (rc) return rc;
+        cb.mag[r] = a.mag_out;
+    }
+    if (combined) {
+        cb.n_hops = 0; cb.n_rows = 1; cb.T = p->T;
+        cb.csr_ptr = p->csr_ptr; cb.csr_res = p->csr_res; cb.csr_lo = p->csr_lo; cb.csr_frac = p->csr_frac;
+        cb.out = (float*)c->d_out.p + comb_off;
+        p->launches++;
+        combine_kernel<<<(unsigned)((p->T + 255) / 256), 256, 0, c->s>>>(cb);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(c->h_out, c->d_out.p, out_tot * sizeof(float), cudaMemcpyDeviceToHost, c->s));
+    CK(cudaStreamSynchronize(c->s));
+    for (int r = 0; r < p->n_res; ++r)
+        if (frames[r]) memcpy(magnitudes[r], c->h_out + out_off[r], (size_t)p->res[r].bins * sizeof(float));
+    if (combined) memcpy(combined, c->h_out + comb_off, (size_t)p->T * sizeof(float));
+    return OMEGA4_OK;
+}
+
+extern "C" int omega4_meter_update(omega4_plan* p, const double* frame, double* state, int fresh, float* meters,
+                                   double* lufs_inst, double* tp_db) {
+    if (!p || !frame || !state || !meters) return fail(OMEGA4_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(p->device));
+    const int W = p->W;
+    StreamCtx* c = stream_ctx(p);
+    // staging layout (doubles): frame [W] | lufs, tp [2] | meters (5 floats in 4 doubles) | state [ST_STATE]
+    const size_t n_d = (size_t)W + 2 + 4 + ST_STATE;
+    int rc = c->ensure64(n_d * sizeof(double)); if (rc) return rc;
+    double* h = c->h64; double* d = (double*)c->d64.p;
+    memcpy(h, frame, (size_t)W * sizeof(double));
+    size_t up = (size_t)W;
+    if (!fresh) { memcpy(h + W + 6, state, ST_STATE * sizeof(double)); }
+    CK(cudaMemcpyAsync(d, h, up * sizeof(double), cudaMemcpyHostToDevice, c->s));
+    if (!fresh) CK(cudaMemcpyAsync(d + W + 6, h + W + 6, ST_STATE * sizeof(double), cudaMemcpyHostToDevice, c->s));
+    {
+        KweightArgs k;
+        memset(&k, 0, sizeof k);
+        k.x = d; k.x_is_f64 = 1; k.ch_stride = 0; k.frame_stride = W; k.frame_off0 = 0;
+        k.n_ch = 1; k.n_frames = 1; k.first_frame = 0; k.frames_per_warp = 1;
+        k.hann = nullptr; k.lufs_out = d + W; k.weighted_out = nullptr;
+        fill_weighting(p, &k);
+        p->launches++;
+        rc = launch_kweight(k, c->s); if (rc) return rc;
+        TruePeakArgs t;
+        memset(&t, 0, sizeof t);
+        t.x = d; t.x_is_f64 = 1; t.ch_stride = 0; t.frame_stride = W; t.frame_off0 = 0;
+        t.n_ch = 1; t.n_frames = 1; t.first_frame = 0; t.rounds = 1;
+        t.window = nullptr; t.twM = p->tw_meter.twM; t.rot = p->tp_rot;
+        fill_truepeak_steps(&t);
+        t.tp_out = d + W + 1;
+        p->launches++;
+        rc = launch_truepeak(t, c->s); if (rc) return rc;
+        StatsArgs st;
+        memset(&st, 0, sizeof st);
+        st.lufs = d + W; st.tp = d + W + 1; st.n_ch = 1; st.n_frames = 1; st.first_frame = 0;
+        st.gate = p->gate; st.out = (float*)(d + W + 2); st.fresh = fresh ? 1 : 0; st.state = d + W + 6;
+        p->launches++;
+        rc = launch_stats(st, c->s); if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h + W, d + W, (6 + ST_STATE) * sizeof(double), cudaMemcpyDeviceToHost, c->s));
+    CK(cudaStreamSynchronize(c->s));
+    if (lufs_inst) *lufs_inst = h[W];
+    if (tp_db) *tp_db = h[W + 1];
+    memcpy(meters, h + W + 2, 5 * sizeof(float));
+    memcpy(state, h + W + 6, ST_STATE * sizeof(double));
+    return OMEGA4_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1677,13 +1925,6 @@ extern "C" int omega4_synth_fill(int device, void* stream, float* out_device, in
 // ------------------------------------------------------------------------------------------
 // application post-processing: combined spectrum -> band_values (omega4_main.py:992-1056)
 // ------------------------------------------------------------------------------------------
-struct omega4_bars {
-    int device = 0, T = 0, n_valid = 0, p_lo = 0, normalize_max = 0;
-    float p_frac = 0.f, scale = 0.8f;
-    int* bands = nullptr; float* gain = nullptr; float* sf = nullptr; float* sfc = nullptr;
-    DevBuf h_spec, h_out, h_peak, h_state, state_in;
-};
-
 extern "C" omega4_bars* omega4_bars_create(const omega4_bars_desc* d, int device) {
     if (!d || !d->bands || d->spectrum_len < 2 || d->n_bars < 1 || d->percentile < 0 || d->percentile > 100) {
         fail(OMEGA4_ERR_INVALID, "bad bars descriptor"); return nullptr;
@@ -1734,50 +1975,31 @@ extern "C" int omega4_bars_run(omega4_bars* b, void* stream, int mem, const floa
     CK(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t rows = (size_t)n_ch * n_hops;
-    BarsArgs a;
-    memset(&a, 0, sizeof a);
-    a.T = b->T; a.n_ch = n_ch; a.n_hops = n_hops; a.n_valid = b->n_valid; a.bands = b->bands; a.gain = b->gain;
-    a.sf = b->sf; a.sfc = b->sfc; a.p_lo = b->p_lo; a.p_frac = b->p_frac; a.scale = b->scale;
-    a.normalize_max = b->normalize_max; a.fresh = (fresh || !state) ? 1 : 0;
     const size_t st_bytes = (size_t)n_ch * (1 + b->n_valid) * sizeof(float);
+    const float* d_spec = spectrum; float* d_out = band_values; float* d_peak = peak_values; float* d_state = state;
+    const int is_fresh = (fresh || !state) ? 1 : 0;
     if (mem == OMEGA4_MEM_HOST) {
         int rc = b->h_spec.ensure(rows * b->T * sizeof(float)); if (rc) return rc;
         rc = b->h_out.ensure(rows * b->n_valid * sizeof(float)); if (rc) return rc;
         CK(cudaMemcpyAsync(b->h_spec.p, spectrum, rows * b->T * sizeof(float), cudaMemcpyHostToDevice, s));
-        a.spec = (const float*)b->h_spec.p; a.bars_out = (float*)b->h_out.p;
-        if (peak_values) { rc = b->h_peak.ensure(rows * b->n_valid * sizeof(float)); if (rc) return rc; a.peaks_out = (float*)b->h_peak.p; }
+        d_spec = (const float*)b->h_spec.p; d_out = (float*)b->h_out.p;
+        if (peak_values) { rc = b->h_peak.ensure(rows * b->n_valid * sizeof(float)); if (rc) return rc; d_peak = (float*)b->h_peak.p; }
         if (state) {
             rc = b->h_state.ensure(st_bytes); if (rc) return rc;
-            if (!a.fresh) CK(cudaMemcpyAsync(b->h_state.p, state, st_bytes, cudaMemcpyHostToDevice, s));
-            a.state = (float*)b->h_state.p;
+            if (!is_fresh) CK(cudaMemcpyAsync(b->h_state.p, state, st_bytes, cudaMemcpyHostToDevice, s));
+            d_state = (float*)b->h_state.p;
         }
-    } else if (mem == OMEGA4_MEM_DEVICE) {
-        a.spec = spectrum; a.bars_out = band_values; a.peaks_out = peak_values; a.state = state;
-    } else {
+    } else if (mem != OMEGA4_MEM_DEVICE) {
         return fail(OMEGA4_ERR_INVALID, "mem must be OMEGA4_MEM_HOST or OMEGA4_MEM_DEVICE");
     }
-    const size_t smem = bars_smem_bytes(b->T, b->n_valid);
-    if (smem > 200 * 1024) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel");
-    if (b->T <= 512) CK(cudaFuncSetAttribute(bars_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(bars_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (b->T > 32 * BARS_MAXV) return fail(OMEGA4_ERR_UNSUPPORTED, "spectrum too long for the bars kernel (max 1024 bins)");
-    a.seg = n_ch >= 1024 ? 4 * BARS_SEG : BARS_SEG;              // fewer warm-up replays when channels alone fill the GPU
-    const long long grid = (long long)n_ch * ((n_hops + a.seg - 1) / a.seg);
-    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "bars grid too large");
-    if (a.state && !a.fresh && n_hops > a.seg) {
-        // the last segment of a channel writes the carried state while segment 0 of the same launch reads it:
-        // segment 0 reads a private copy
-        int rc = b->state_in.ensure(st_bytes); if (rc) return rc;
-        CK(cudaMemcpyAsync(b->state_in.p, a.state, st_bytes, cudaMemcpyDeviceToDevice, s));
-        a.state_in = (const float*)b->state_in.p;
+    {
+        int rc = bars_launch(b, s, d_spec, n_ch, n_hops, d_state, is_fresh, d_out, d_peak, &b->state_in);
+        if (rc) return rc;
     }
-    if (b->T <= 512) bars_kernel<16><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
-    else bars_kernel<32><<<(unsigned)grid, BARS_WARPS * 32, smem, s>>>(a);
-    CK(cudaGetLastError());
     if (mem == OMEGA4_MEM_HOST) {
-        CK(cudaMemcpyAsync(band_values, a.bars_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (peak_values) CK(cudaMemcpyAsync(peak_values, a.peaks_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (state) CK(cudaMemcpyAsync(state, a.state, st_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(band_values, d_out, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (peak_values) CK(cudaMemcpyAsync(peak_values, d_peak, rows * b->n_valid * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (state) CK(cudaMemcpyAsync(state, d_state, st_bytes, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
     return OMEGA4_OK;

@@ -29,6 +29,7 @@ FLAG_NO_BLOCKDFT = 8
 FLAG_NO_TENSOR = 16
 FLAG_TENSOR = 32
 FLAG_SERIAL_STATS = 64
+FLAG_FRESH_BARS = 128
 ABI_VERSION = 2
 WATERFALL_STATE = 41
 
@@ -40,6 +41,7 @@ EXPORTS = (
     "omega4_synth_fill", "omega4_plan_launches", "omega4_plan_kernel_times",
     "omega4_analyze_s16", "omega4_plan_set_weighting", "omega4_bass_bars", "omega4_bars_create", "omega4_bars_destroy", "omega4_bars_count", "omega4_bars_run",
     "omega4_waterfall", "omega4_plan_set_gate_threshold",
+    "omega4_analyze_io", "omega4_stream_hop", "omega4_meter_update",
 )
 
 
@@ -83,6 +85,18 @@ class BarsDesc(C.Structure):
         ("percentile", C.c_double),
         ("scale", C.c_float),
         ("normalize_max", C.c_int),
+    ]
+
+
+class IO(C.Structure):
+    """omega4_io (include/omega4_cuda.h)."""
+    _fields_ = [
+        ("samples", C.c_void_p), ("frames_s16", C.c_void_p), ("n_interleaved", C.c_int),
+        ("stride", C.c_longlong), ("n_ch", C.c_int), ("n_hops", C.c_int), ("hist", C.c_int),
+        ("combined", C.c_void_p), ("magnitudes", C.POINTER(C.c_void_p)), ("meters", C.c_void_p),
+        ("lufs_inst", C.c_void_p), ("tp_db", C.c_void_p), ("meter_state", C.c_void_p),
+        ("bars", C.c_void_p), ("band_values", C.c_void_p), ("peak_values", C.c_void_p), ("bars_state", C.c_void_p),
+        ("flags", C.c_int),
     ]
 
 
@@ -130,6 +144,12 @@ def lib() -> C.CDLL:
         l.omega4_rfft_batch.argtypes = [ip, vp, ip, vp, ip, ip, vp, vp, vp]
         l.omega4_band_map.restype = ip
         l.omega4_band_map.argtypes = [ip, vp, ip, vp, ip, ip, vp, ip, vp, vp, ip]
+        l.omega4_analyze_io.restype = ip
+        l.omega4_analyze_io.argtypes = [vp, vp, ip, C.POINTER(IO)]
+        l.omega4_stream_hop.restype = ip
+        l.omega4_stream_hop.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp]
+        l.omega4_meter_update.restype = ip
+        l.omega4_meter_update.argtypes = [vp, vp, vp, ip, vp, vp, vp]
         l.omega4_waterfall.restype = ip
         l.omega4_waterfall.argtypes = [ip, vp, ip, vp, ip, ip, ip, ip, ip, ip, ip, C.c_float, vp, ip, vp, vp, vp]
         l.omega4_plan_set_gate_threshold.restype = ip

@@ -17,6 +17,7 @@ rectangular-window quirk (:179-193) and the per-call ``magnitude.copy()`` owners
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import threading
 import time
@@ -108,8 +109,10 @@ class CircularBuffer:
         with self._lock:
             if self.samples_written < length:
                 return None
-            idx = (self.write_pos - length + np.arange(length)) % self.size
-            return self.buffer[idx]
+            start = self.write_pos - length                     # same samples as the reference's modular index, two slices
+            if start >= 0:
+                return self.buffer[start:self.write_pos].copy()
+            return np.concatenate((self.buffer[start:], self.buffer[:self.write_pos]))
 
     def reset(self):
         with self._lock:
@@ -137,6 +140,8 @@ class MultiResolutionFFT:
             FFTConfig((5000, 20000), 1024, 256, 1.5),
         ]
         self._plans: Dict[Tuple[bool, int], AnalysisPlan] = {}
+        self._combine_bins = 1024                           # combine_results_optimized's default target_bins (:335)
+        self._last = None
         self._setup_windows()
         self._setup_buffers()
         self._setup_frequency_arrays()
@@ -149,6 +154,7 @@ class MultiResolutionFFT:
         for p in getattr(self, "_plans", {}).values():
             p.close()
         self._plans = {}
+        self._last = None
 
     def _setup_windows(self):
         self.windows = {i: tables.multires_window(c.window_type.value if isinstance(c.window_type, WindowType)
@@ -199,24 +205,29 @@ class MultiResolutionFFT:
             frames.append(a)
         results: Dict[int, FFTResult] = {}
         if ready:
-            plan = self._plan(apply_weighting, 512)
-            # one launch per ready resolution: a single hop whose window is the ring's latest N samples
-            nmax = max(c.fft_size for c in self.configs)
-            row = np.zeros((1, nmax), dtype=np.float32)
-            mags_all = {}
-            # all rings hold the same stream, so the longest ready frame contains the others unless
-            # the caller wrote different data per ring (it cannot); still, honour each ring's own frame.
+            # ONE host round trip for every ready resolution: the frames go up together, the magnitudes (and the
+            # combination over exactly these resolutions, for the combine_results_optimized call that follows in
+            # the application, omega4_main.py:707-714) come back together (omega4_stream_hop)
+            plan = self._plan(apply_weighting, self._combine_bins)
+            n_res = len(self.configs)
+            fptr = (C.c_void_p * n_res)()
+            mptr = (C.c_void_p * n_res)()
+            mags = {}
+            keep = []
             for i, a in zip(ready, frames):
-                n = len(a)
-                row[0, nmax - n:] = a
-                mags = [None] * len(self.configs)
-                mags[i] = np.empty((1, 1, n // 2 + 1), np.float32)
-                rc = N.lib().omega4_analyze(plan.handle, None, N.MEM_HOST, row.ctypes.data + (nmax - plan.hop) * 4,
-                                            nmax, 1, 1, n - plan.hop, None, N.ptr_array(mags), None, None, None, None, 0)
-                N.check(rc, "omega4_analyze")
-                mags_all[i] = mags[i][0, 0]
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                keep.append(a)
+                mags[i] = np.empty(len(a) // 2 + 1, np.float32)
+                fptr[i] = a.ctypes.data
+                mptr[i] = mags[i].ctypes.data
+            comb = np.empty(self._combine_bins, np.float32)
+            rc = N.lib().omega4_stream_hop(plan.handle, fptr, mptr, comb.ctypes.data)
+            N.check(rc, "omega4_stream_hop")
             for i in ready:
-                results[i] = FFTResult(magnitude=mags_all[i].copy(), frequencies=self.freq_arrays[i], config_index=i)
+                results[i] = FFTResult(magnitude=mags[i], frequencies=self.freq_arrays[i], config_index=i)
+            # remembered so that combine_results_optimized(results) can hand the combination back without another
+            # round trip -- only if the caller passes these very magnitudes, unmodified (compared value by value)
+            self._last = (bool(apply_weighting), self._combine_bins, {i: mags[i].copy() for i in ready}, comb)
         self.processing_stats["total_calls"] += 1
         self.processing_stats["total_time"] += time.perf_counter() - start
         return results
@@ -225,11 +236,18 @@ class MultiResolutionFFT:
         if not results:
             logger.warning("No FFT results to combine")
             return np.zeros(target_bins), np.linspace(0, self.max_freq, target_bins)
+        last = self._last
+        if last is not None and last[1] == target_bins and len(results) == len(last[2]) and \
+                all(r.config_index in last[2] and np.array_equal(r.magnitude, last[2][r.config_index]) for r in results.values()):
+            return last[3].copy(), np.linspace(0, self.max_freq, target_bins)
+        self._combine_bins = int(target_bins)               # the next process_audio_chunk combines for this length
         plan = self._plan(True, target_bins)
         mags = [None] * len(self.configs)
         for r in results.values():
             mags[r.config_index] = np.asarray(r.magnitude, dtype=np.float32)
         combined = plan.combine_host(mags, 1)[0]
+        self._last = (True, int(target_bins), {r.config_index: np.array(r.magnitude, dtype=np.float32, copy=True) for r in results.values()},
+                      combined.copy())
         return combined, np.linspace(0, self.max_freq, target_bins)
 
     # -- bookkeeping API of the reference ------------------------------------------------------

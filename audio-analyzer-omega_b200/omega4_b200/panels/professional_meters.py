@@ -48,6 +48,7 @@ class ProfessionalMetering:
         self._plan = _meter_plan(sample_rate, device)
         self._state = np.zeros((1, N.METER_STATE_DOUBLES), dtype=np.float64)
         self._fresh = True
+        self._out = np.zeros(N.N_METERS, dtype=np.float32)
         self.weighting_mode = "K"
         self.gate_threshold = -70.0
         c = self._plan.kw_coeffs
@@ -116,12 +117,18 @@ class ProfessionalMetering:
         """(:231-281) returns the same mutable dict object on every call, as the reference does."""
         if len(audio_data) == 0:
             return self.current_lufs
-        f = np.asarray(audio_data, dtype=np.float64)
-        li, tp, _ = self._mode_plan().meter_frames_host(f)
-        self._plan.set_gate_threshold(self.gate_threshold)       # read on every call, as :267 does (plans are shared)
-        out = self._plan.meter_stats_host(li, tp, state=self._state, fresh=self._fresh)
+        f = np.ascontiguousarray(audio_data, dtype=np.float64)
+        plan = self._mode_plan()
+        if f.shape != (plan.meter_window,):
+            raise N.Omega4CudaError(f"meter frames must have {plan.meter_window} samples (got {f.shape}); "
+                                    "other lengths are not implemented on the GPU and there is no CPU fallback")
+        plan.set_gate_threshold(self.gate_threshold)             # read on every call, as :267 does (plans are shared)
+        # weighting + mean square, true peak and the deque statistics in one host round trip
+        rc = N.lib().omega4_meter_update(plan.handle, f.ctypes.data, self._state.ctypes.data, 1 if self._fresh else 0,
+                                         self._out.ctypes.data, None, None)
+        N.check(rc, "omega4_meter_update")
         self._fresh = False
-        for k, v in zip(METER_KEYS, out[0, 0]):
+        for k, v in zip(METER_KEYS, self._out):
             self.current_lufs[k] = float(v)
         return self.current_lufs
 

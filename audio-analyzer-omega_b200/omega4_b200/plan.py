@@ -250,6 +250,35 @@ class AnalysisPlan:
                                     N.checked(meter_state, "float64", n_ch * N.METER_STATE_DOUBLES, "meter_state"), flags)
         N.check(rc, "omega4_analyze")
 
+    def analyze_io(self, mem: int, n_ch: int, n_hops: int, stride: int, samples=None, frames_s16=None, n_interleaved: int = 1,
+                   hist: int = 0, combined=None, meters=None, meter_state=None, bars=None, band_values=None, peak_values=None,
+                   bars_state=None, flags: int = 0, stream=None):
+        """``omega4_analyze_io``: the whole path with the application's post-processing fused behind the combine
+        step.  ``samples`` (float32 planar rows) or ``frames_s16`` (interleaved int16) are numpy arrays / torch
+        tensors / raw addresses of the first NEW sample; ``bars`` is a ``SpectrumPostProcessor`` (or its native
+        handle).  Host mode is synchronous, device mode asynchronous on ``stream``."""
+        io = N.IO()
+        io.samples, io.frames_s16 = N.ptr(samples), N.ptr(frames_s16)
+        io.n_interleaved, io.stride, io.n_ch, io.n_hops, io.hist = int(n_interleaved), int(stride), int(n_ch), int(n_hops), int(hist)
+        rows = n_ch * n_hops
+        io.combined = N.checked(combined, "float32", rows * self.target_bins, "combined")
+        io.magnitudes = None
+        io.meters = N.checked(meters, "float32", rows * N.N_METERS, "meters")
+        io.lufs_inst = io.tp_db = None
+        io.meter_state = N.checked(meter_state, "float64", n_ch * N.METER_STATE_DOUBLES, "meter_state")
+        if bars is not None:
+            handle = bars._ensure() if hasattr(bars, "_ensure") else bars
+            nv = int(N.lib().omega4_bars_count(handle))
+            io.bars = handle
+            io.band_values = N.checked(band_values, "float32", rows * nv, "band_values")
+            io.peak_values = N.checked(peak_values, "float32", rows * nv, "peak_values")
+            io.bars_state = N.checked(bars_state, "float32", n_ch * (1 + nv), "bars_state")
+        io.flags = int(flags)
+        if mem == N.MEM_DEVICE and stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        N.check(N.lib().omega4_analyze_io(self.handle, stream, mem, C.byref(io)), "omega4_analyze_io")
+
     # ------------------------------------------------------------------ int16 wire format (SURVEY.md section 8f rank 4)
     def analyze_s16_host(self, frames: np.ndarray, hist_frames: int = 0, want_combined: bool = True,
                          want_meters: bool = True, want_series: bool = False, flags: int = 0) -> Dict[str, object]:

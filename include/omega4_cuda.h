@@ -64,6 +64,8 @@ extern "C" {
 #define OMEGA4_FLAG_SERIAL_STATS 64               /* keep the deque-statistics kernel on the caller's stream (default: it
                                                     runs on an internal side stream underneath the FFT kernels) */
 
+#define OMEGA4_FLAG_FRESH_BARS 128                /* omega4_analyze_io: ignore bars_state contents on entry */
+
 typedef struct omega4_plan omega4_plan;
 
 /* Everything that defines the reference's behaviour is DATA computed on the host with the
@@ -153,6 +155,53 @@ int omega4_analyze_s16(omega4_plan* plan, void* stream, int mem,
                        float* combined, float* const* magnitudes, float* meters,
                        double* lufs_inst, double* tp_db, double* meter_state, int flags);
 
+/* The same path with every optional input / output in one descriptor, plus the application's post-processing
+ * fused behind the combine step: what process_audio_spectrum hands the display is `band_values`
+ * (omega4_main.py:992-1056 -> omega4_bars_*), so a caller that only draws bars and meters asks for
+ * band_values + meters and never moves the combined spectrum off the device.
+ *   samples / frames_s16   exactly one is non-NULL (float32 planar rows, or interleaved int16 as omega4_analyze_s16)
+ *   stride                 ch_stride (float units) or stream_stride (int16 units); n_ch planar channels in total
+ *   bars                   an omega4_bars object on the plan's device with spectrum_len == target_bins, or NULL
+ *   band_values, peak_values  [n_ch][n_hops][omega4_bars_count(bars)] (peak_values may be NULL)
+ *   bars_state             [n_ch][1 + count] float32 smoothing state carried between calls, or NULL (fresh)
+ * Every other field means what the omega4_analyze argument of the same name means. */
+typedef struct omega4_bars omega4_bars;
+typedef struct omega4_io {
+    const float* samples;
+    const short* frames_s16;
+    int n_interleaved;
+    long long stride;
+    int n_ch, n_hops, hist;
+    float* combined;
+    float* const* magnitudes;
+    float* meters;
+    double* lufs_inst;
+    double* tp_db;
+    double* meter_state;
+    omega4_bars* bars;
+    float* band_values;
+    float* peak_values;
+    float* bars_state;
+    int flags;
+} omega4_io;
+int omega4_analyze_io(omega4_plan* plan, void* stream, int mem, const omega4_io* io);
+
+/* ---- streaming entry points: one round trip per application frame -------------------------- */
+/* MultiResolutionFFT.process_audio_chunk (multi_resolution_fft.py:228-302) for the resolutions whose ring has
+ * filled, and combine_results_optimized (:335-408) over exactly those, in ONE host round trip: frames[r] is the
+ * latest fft_size[r] samples of resolution r's ring (HOST float32) or NULL when that ring is not ready;
+ * magnitudes[r] receives |X| x weights (fft_size[r]/2+1 values); combined ([target_bins], may be NULL) the
+ * combination of the ready resolutions (zeros when none is).  Synchronous; staging buffers are pinned and
+ * owned by the plan. */
+int omega4_stream_hop(omega4_plan* plan, const float* const* frames, float* const* magnitudes, float* combined);
+
+/* ProfessionalMetering.calculate_lufs (professional_meters.py:231-281) on ONE float64 frame of
+ * OMEGA4_METER_WINDOW samples in one host round trip: weighting + mean square, true peak, deque statistics.
+ * state: HOST [OMEGA4_METER_STATE_DOUBLES], read (unless fresh) and written; meters: HOST float[5]
+ * (M, S, I, LRA, TP); lufs_inst / tp_db: this frame's values, or NULL. */
+int omega4_meter_update(omega4_plan* plan, const double* frame, double* state, int fresh, float* meters,
+                        double* lufs_inst, double* tp_db);
+
 /* combine_results_optimized (multi_resolution_fft.py:335-408) on caller-supplied magnitudes:
  * magnitudes[r] = [n_rows][N_r/2+1] or NULL when resolution r is absent from `results`. */
 int omega4_combine(omega4_plan* plan, void* stream, int mem,
@@ -222,7 +271,6 @@ int omega4_synth_fill(int device, void* stream, float* out_device, int n_streams
  * mel band mean -> sqrt -> clamp [0,1] over PrecomputedFrequencyMapper's band table (the loop stops
  * at the first band reaching past the spectrum, :1012-1013), per-band exponential smoothing
  * against the previous frame (:1041-1056).  Tables are host pointers, copied at creation. */
-typedef struct omega4_bars omega4_bars;
 typedef struct omega4_bars_desc {
     int spectrum_len;              /* T: length of one combined spectrum (self.bars) */
     int n_bars;                    /* entries in `bands` */

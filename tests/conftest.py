@@ -63,3 +63,34 @@ def assert_spectrum_close(got, ref, tol_db=0.01, rel_floor_db=-80.0, label=""):
     lim = np.broadcast_to(floor * (10 ** (tol_db / 20.0) - 1.0) + 1e-12, r2.shape)
     bad = np.abs(g2 - r2) > lim
     assert not (bad & ~sig).any(), f"{label}: absolute error above floor in {int((bad & ~sig).sum())} quiet bins"
+
+
+def transform_peaks(ref, configs, n_hops, target_bins=512, max_freq=20000.0):
+    """Per (hop, target bin): the largest magnitude (all N/2+1 bins) of the transform that feeds the bin, from
+    ``oracle.analyze_channel(..., keep_magnitudes=True)``.  A combined row's own maximum says nothing about the
+    float32 noise floor of a long transform whose window holds a full-scale tone outside the bins it contributes."""
+    tf = np.linspace(0.0, max_freq, target_bins)
+    peak = np.zeros((n_hops, target_bins))
+    for i, cfg in enumerate(configs):
+        lo, hi = cfg[0]
+        first, m = ref["magnitudes"][i]
+        col = np.zeros(n_hops)
+        col[first:first + len(m)] = m.max(axis=1)
+        sel = (tf >= lo) & (tf <= hi)
+        peak[:, sel] = np.maximum(peak[:, sel], col[:, None])
+    return peak
+
+
+def assert_spectrum_close_per_transform(got, ref, peaks, tol_db=0.01, rel_floor_db=-80.0, label=""):
+    """The same gate as ``assert_spectrum_close`` with the floor counted from the feeding transform's largest
+    magnitude (``transform_peaks``) instead of the row maximum."""
+    g = np.asarray(got, dtype=np.float64)
+    r = np.asarray(ref, dtype=np.float64)
+    floor = np.asarray(peaks, dtype=np.float64) * 10 ** (rel_floor_db / 20.0)
+    sig = (r >= np.maximum(floor, 1e-30)) & (r > 0)
+    if sig.any():
+        err = np.abs(db(g[sig], 1e-30) - db(r[sig], 1e-30))
+        assert err.max() <= tol_db, f"{label}: max dB err {err.max():.5f} over {int(sig.sum())} values within {-rel_floor_db:g} dB of their transform's maximum"
+    lim = floor * (10 ** (tol_db / 20.0) - 1.0) + 1e-12
+    bad = (np.abs(g - r) > lim) & ~sig
+    assert not bad.any(), f"{label}: absolute error above the floor in {int(bad.sum())} quiet values"

@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import assert_spectrum_close
+from conftest import assert_spectrum_close, assert_spectrum_close_per_transform, transform_peaks
 from oracle import oracle_np as O
 
 pytestmark = pytest.mark.gpu
@@ -93,8 +93,15 @@ def test_multires_96k_adversarial_stream_golden(golden):
     x = g["x"]
     f0 = int(g["combined_first"])
     plan = AnalysisPlan(96000, CONFIG5_96K, 512)
+    # largest magnitude of the transform behind every target bin, per hop (the floor of the gate counts from it)
+    ref = O.analyze_channel(x, 96000, O.CONFIG5_96K, keep_magnitudes=True)
+    np.testing.assert_allclose(ref["combined"][f0:, :32], g["combined_low"], rtol=3e-6, atol=1e-9)
+    peaks = transform_peaks(ref, O.CONFIG5_96K, len(x) // HOP)
     got = {}
-    for tag, fl in (("default", 0), ("fft", N.FLAG_NO_BLOCKDFT)):
+    # The tensor-core path carries an error floor of a few 1e-7 of the transform's largest magnitude (the
+    # tensor-core accumulator truncates; tests/tools/tone_leak_probe.py, profiles/r02_tone_leak.txt): next to a
+    # full-scale tone it holds 0.01 dB down to about -65 dB, the FFT kernel well below -80 dB.
+    for tag, fl, floor_db in (("default", 0, -60.0), ("fft", N.FLAG_NO_BLOCKDFT, -80.0)):
         out = plan.analyze_host(x[None, :], want_meters=False, flags=N.FLAG_TIME_KERNELS | fl)
         names = _names(plan)
         if tag == "default":
@@ -106,14 +113,18 @@ def test_multires_96k_adversarial_stream_golden(golden):
         got[tag] = comb
         low = comb[f0:, :32]
         assert np.array_equal(low == 0, g["combined_low"] == 0), tag
-        # bins 1..5 come from the 32768 / 16384 transforms: the gate counts from the largest value they show
-        for k in range(low.shape[0]):
-            assert_spectrum_close(low[k, 1:6], g["combined_low"][k, 1:6], TOL_DB, label=f"{tag} hop {f0 + k} sparse bins")
+        # target bins 1..5 come from the 32768 / 16384 transforms (tensor cores by default)
+        assert_spectrum_close_per_transform(low[:, 1:6], g["combined_low"][:, 1:6], peaks[f0:, 1:6], TOL_DB, floor_db,
+                                            label=f"{tag} sparse bins")
+        # the other four resolutions (full FFT kernels in both modes).  Next to two strong pure tones the float32
+        # noise of ANY fp32 transform -- the reference's pocketfft included -- is ~1e-7 of the largest magnitude,
+        # i.e. 0.009 dB at -80 dB: the gate for this adversarial stream sits at -70 dB
         for k in (75, 130, 149):
-            assert_spectrum_close(comb[k], g[f"combined_h{k}"], TOL_DB, label=f"{tag} hop {k}")
+            assert_spectrum_close_per_transform(comb[k, 6:], g[f"combined_h{k}"][6:], peaks[k, 6:], TOL_DB, -70.0,
+                                                label=f"{tag} hop {k}")
         assert np.all(comb[:63, 1] == 0) and comb[63, 1] > 0           # 32768 / 512 - 1: first filled hop
     scale = got["fft"].max(axis=1, keepdims=True) + 1e-20
-    assert (np.abs(got["fft"] - got["default"]) / scale).max() < 2e-5
+    assert (np.abs(got["fft"] - got["default"]) / scale).max() < 1e-4
     # magnitudes of the two largest transforms (API-faithful output) at the probe hops
     out = plan.analyze_host(x[None, :], want_meters=False, want_magnitudes=True)
     for k in (75, 130, 149):
@@ -158,7 +169,7 @@ def test_exact_windowing_edge_shapes_at_64_blocks(golden):
     scale = full.max(axis=2, keepdims=True) + 1e-20
     assert np.array_equal(tiled == 0, one == 0)
     assert (np.abs(tiled - one) / scale).max() < 2e-6              # same kernels, different tile cuts: fp32 summation order only
-    assert (np.abs(one - full) / scale).max() < 2e-5
+    assert (np.abs(one - full) / scale).max() < 1e-4               # against the full FFT: the tensor-core path's error floor
     plan.close()
 
 
@@ -307,7 +318,11 @@ def test_gate_threshold_is_honoured(plan48):
         got = plan48.meter_stats_host(li, tp, fresh=True)[0]
         st = O.OracleMeterStats()
         st.gate = gate
-        want = np.array([[st.push(a, b)[k] for k in O.METER_KEYS] for a, b in zip(li, tp)])
+        want = []
+        for a, b in zip(li, tp):
+            d = st.push(a, b)                                          # one push per frame (the dict is reused)
+            want.append([d[k] for k in O.METER_KEYS])
+        want = np.array(want)
         assert np.abs(got - want).max() <= 1e-4, gate
     plan48.set_gate_threshold(-70.0)
     from omega4_b200.panels.professional_meters import ProfessionalMetering
@@ -348,3 +363,88 @@ def plan48():
     p = AnalysisPlan(48000, BASELINE_CONFIGS, 512)
     yield p
     p.close()
+
+
+# ------------------------------------------------------------------ omega4_analyze_io: fused band values, one descriptor
+def test_analyze_io_fused_band_values_match_the_two_step_path(plan48):
+    """int16 host input -> band_values + meters without the combined spectrum ever leaving the device: identical
+    to omega4_analyze_s16 followed by omega4_bars_run (same kernels, same order), host and device mode, with the
+    smoothing and meter states carried over time tiles."""
+    import torch
+    from omega4_b200 import _native as N
+    from omega4_b200.app.spectrum_post import SpectrumPostProcessor
+    from omega4_b200.batch.synth import synth_streams
+    n_hops, n_streams = 90, 3
+    x = synth_streams(n_streams, 2, n_hops * HOP)                          # [3, 2, n]
+    x16 = np.ascontiguousarray(np.clip(np.round(x.transpose(0, 2, 1) * 32767.0), -32768, 32767).astype(np.int16))   # [3, n, 2]
+    two = plan48.analyze_s16_host(x16, want_combined=True, want_meters=True)
+    post = SpectrumPostProcessor(512)
+    want_bars, want_peaks = post.process_host(two["combined"], want_peaks=True)
+    nv, n_ch = post.n_valid, n_streams * 2
+    band = np.empty((n_ch, n_hops, nv), np.float32)
+    peak = np.empty_like(band)
+    met = np.empty((n_ch, n_hops, 5), np.float32)
+    plan48.analyze_io(N.MEM_HOST, n_ch, n_hops, x16.strides[0] // 2, frames_s16=x16, n_interleaved=2, meters=met,
+                      bars=post, band_values=band, peak_values=peak)
+    assert np.array_equal(band, want_bars) and np.array_equal(peak, want_peaks) and np.array_equal(met, two["meters"])
+    # float input, combined requested as well
+    xf = np.ascontiguousarray(x16.transpose(0, 2, 1).reshape(n_ch, -1).astype(np.float32) / 32768.0)
+    comb = np.empty((n_ch, n_hops, 512), np.float32)
+    band2 = np.empty_like(band)
+    plan48.analyze_io(N.MEM_HOST, n_ch, n_hops, xf.shape[1], samples=xf, combined=comb, bars=post, band_values=band2)
+    assert np.array_equal(comb, two["combined"]) and np.array_equal(band2, want_bars)
+    # device mode in two time tiles with carried states == one shot
+    sb_state = torch.zeros((n_ch, 1 + nv), device="cuda")
+    m_state = torch.zeros((n_ch, N.METER_STATE_DOUBLES), dtype=torch.float64, device="cuda")
+    d16 = torch.from_numpy(x16).cuda()
+    outs, mets = [], []
+    hist = 0
+    for a, b in ((0, 50), (50, 90)):
+        n = b - a
+        bv = torch.empty((n_ch, n, nv), device="cuda")
+        mv = torch.empty((n_ch, n, 5), device="cuda")
+        base = d16.data_ptr() + a * HOP * 2 * 2
+        plan48.analyze_io(N.MEM_DEVICE, n_ch, n, d16.stride(0), frames_s16=base, n_interleaved=2, hist=a * HOP, meters=mv,
+                          meter_state=m_state, bars=post, band_values=bv, bars_state=sb_state,
+                          flags=(N.FLAG_FRESH_METERS | N.FLAG_FRESH_BARS) if a == 0 else 0)
+        outs.append(bv)
+        mets.append(mv)
+    torch.cuda.synchronize()
+    tiled = torch.cat(outs, dim=1).cpu().numpy()
+    assert np.abs(tiled - want_bars).max() <= 1e-6                     # tile cut changes the GEMM's row tiling: fp32 order
+    assert np.array_equal(torch.cat(mets, dim=1).cpu().numpy(), two["meters"])
+    with pytest.raises(N.Omega4CudaError):
+        plan48.analyze_io(N.MEM_HOST, n_ch, n_hops, xf.shape[1], samples=xf, frames_s16=x16, meters=met)
+    with pytest.raises(N.Omega4CudaError):
+        plan48.analyze_io(N.MEM_HOST, n_ch, n_hops, xf.shape[1], samples=xf, bars=post, band_values=None)
+    post.close()
+
+
+def test_streaming_shims_one_round_trip(golden):
+    """process_audio_chunk hands back the combination with the magnitudes; combine_results_optimized returns it
+    only for those very magnitudes (otherwise it recomputes), and calculate_lufs is one call."""
+    from omega4_b200.audio.multi_resolution_fft import MultiResolutionFFT
+    from omega4_b200.plan import AnalysisPlan, DEFAULT_CONFIGS
+    g = golden("multires_default.npz")
+    x = g["x"]
+    mr = MultiResolutionFFT(48000)
+    plan = AnalysisPlan(48000, DEFAULT_CONFIGS, 512)
+    for k in range(12):
+        res = mr.process_audio_chunk(x[k * HOP:(k + 1) * HOP])
+        if not res:
+            continue
+        c1, f1 = mr.combine_results_optimized(res, target_bins=512)
+        mags = [res[i].magnitude if i in res else None for i in range(4)]
+        want = plan.combine_host(mags, 1)[0]
+        assert np.array_equal(c1, want), k
+        launches = mr._plan(True, 512).launches
+        c2, _ = mr.combine_results_optimized(res, target_bins=512)          # cached: no kernel launch
+        assert np.array_equal(c2, want) and mr._plan(True, 512).launches == launches
+        res[max(res)].magnitude[200] *= 2.0                                 # caller edits a magnitude inside its range: recomputed
+        c3, _ = mr.combine_results_optimized(res, target_bins=512)
+        mags = [res[i].magnitude if i in res else None for i in range(4)]
+        assert np.array_equal(c3, plan.combine_host(mags, 1)[0]) and not np.array_equal(c3, want)
+        c4, _ = mr.combine_results_optimized(res, target_bins=256)          # another length: recomputed
+        assert c4.shape == (256,)
+        mr._combine_bins = 512
+    plan.close()
