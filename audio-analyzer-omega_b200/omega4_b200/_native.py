@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 LIB_NAME = "libomega4_cuda.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+#: OMEGA4_CUDA_LIB: developer override for A/B measurements of two builds on the same box
+LIB_PATH = os.environ.get("OMEGA4_CUDA_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 OK = 0
 MEM_HOST = 0

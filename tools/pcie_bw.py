@@ -68,23 +68,33 @@ def both():
         h_out.copy_(d_b, non_blocking=True)
 
 
+def e2e_mix():
+    """bench.py's e2e traffic mix: int16 samples up (2 B per sample), float32 result rows down (4 B per sample's
+    worth of spectrum): 1 byte up for every 2 bytes down, both directions busy at once."""
+    with torch.cuda.stream(s1):
+        d_a[: n // 2].copy_(h_in[: n // 2], non_blocking=True)
+    with torch.cuda.stream(s2):
+        h_out.copy_(d_b, non_blocking=True)
+
+
 res = {}
-for name, fn, nbytes in (("h2d", h2d, gb), ("d2h", d2h, gb), ("duplex_each_direction", both, gb)):
+for name, fn, nbytes in (("h2d", h2d, gb), ("d2h", d2h, gb), ("duplex_each_direction", both, gb), ("e2e_mix_total", e2e_mix, 1.5 * gb)):
     t = timeit(fn)                                 # every rank measures the same window: max over ranks = common time
     res[name] = nbytes / t
 if world > 1:
-    vals = torch.tensor([res["h2d"], res["d2h"], res["duplex_each_direction"]], dtype=torch.float64)
+    vals = torch.tensor([res["h2d"], res["d2h"], res["duplex_each_direction"], res["e2e_mix_total"]], dtype=torch.float64)
     allv = [torch.zeros_like(vals) for _ in range(world)]
     dist.all_gather(allv, vals)
     allv = torch.stack(allv)
 else:
-    allv = torch.tensor([[res["h2d"], res["d2h"], res["duplex_each_direction"]]], dtype=torch.float64)
+    allv = torch.tensor([[res["h2d"], res["d2h"], res["duplex_each_direction"], res["e2e_mix_total"]]], dtype=torch.float64)
 if rank == 0:
     out = {"gpus": world, "numa": numa, "buffer_gib": 1}
-    for j, name in enumerate(("h2d", "d2h", "duplex_each_direction")):
+    for j, name in enumerate(("h2d", "d2h", "duplex_each_direction", "e2e_mix_total")):
         col = allv[:, j]
         out[name] = {"per_gpu_min_gbs": float(col.min()), "per_gpu_mean_gbs": float(col.mean()), "aggregate_gbs": float(col.sum())}
     out["duplex_bus_total_gbs"] = 2 * out["duplex_each_direction"]["aggregate_gbs"]
+    out["note"] = "e2e_mix_total = bytes in both directions per second with 1 byte up per 2 bytes down (bench.py's e2e leg): its bus_gbs ceiling"
     print(json.dumps(out), flush=True)
 if world > 1:
     dist.destroy_process_group()
