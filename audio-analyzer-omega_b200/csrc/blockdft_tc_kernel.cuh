@@ -1,7 +1,7 @@
 // blockdft_tc_kernel.cuh -- the hop-block partial DFT GEMM of blockdft_kernel.cuh on the 5th-gen
 // tensor cores: tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, 3xTF32 split precision.
 //
-//   Q[blocks x cols] = X[blocks x hop] . E[hop x cols]            (cols <= 1024: up to four 256-column tiles)
+//   Q[blocks x cols] = X[blocks x hop] . E[hop x cols]            (cols <= 2048: up to eight 256-column tiles)
 //
 // TF32 keeps 11 significant bits, far too few for the 0.01 dB parity bar next to strong peaks, so
 // both operands are split exactly,  x = x_hi + x_lo,  e = e_hi + e_lo  (hi = the top 11 bits, lo = the
@@ -37,6 +37,7 @@ constexpr int TC_BM = 128 * TC_MH;  // hop blocks per CTA
 constexpr int TC_BN = 256 / TC_MH;  // columns per CTA (UMMA N)
 constexpr int TC_KC = 16;           // samples per K chunk: 64-byte rows
 constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_GROUPS = 64;     // 32-column groups of the fused epilogue's tables: up to 2048 GEMM columns
 #ifndef TC_EXPERIMENT_KS
 #define TC_EXPERIMENT_KS 2          // timing experiments only: 1 issues half of the MMAs (wrong results)
 #endif
@@ -55,7 +56,7 @@ struct BlockDftTcArgs {
     int hop;                   // K, multiple of TC_KC
     int n_ch;
     int j0, nb;
-    int n_halves;              // column tiles of TC_BN (1 .. 4)
+    int n_halves;              // column tiles of TC_BN (1 .. 8)
     const uint8_t* Eimg;       // [n_halves][hop/KC][2 (hi, lo)][TC_B_BYTES] pre-swizzled operand images
     float* Q;                  // [n_ch][nb][qs]
     int qs;                    // TC_BN * n_halves
@@ -66,10 +67,10 @@ struct BlockDftTcArgs {
     float2* X;                 // nullptr: plain Q output
     int n_frames;              // frames (= hops) per channel; frame f ends with hop block f
     int nkx;                   // bins per frame over all fused resolutions
-    short gB[32];              // per 32-column group (n_halves * 8): block positions per bin (2, 4, 8, 16; 0 = unused group)
-    short gX[32];              // per group: index of its first bin in [0, nkx)
-    short gN[32];              // per group: bins present (<= 16 / B)
-    short gS[32];              // per group: frame shift.  A transform of more than 16 hop blocks (N / hop = 32, 64) spreads a
+    short gB[TC_MAX_GROUPS];   // per 32-column group (n_halves * 8): block positions per bin (2, 4, 8, 16; 0 = unused group)
+    short gX[TC_MAX_GROUPS];   // per group: index of its first bin in [0, nkx)
+    short gN[TC_MAX_GROUPS];   // per group: bins present (<= 16 / B)
+    short gS[TC_MAX_GROUPS];   // per group: frame shift.  A transform of more than 16 hop blocks (N / hop = 32, 64) spreads a
                                // bin over N / hop / 16 groups of 16 positions; the group holding positions 16 p .. 16 p + 15
                                // adds its partial sum to the frame that ends gS = N / hop - 16 (p + 1) blocks after the
                                // group's own last row, always with atomicAdd (several groups feed one X element); -1 = plain group

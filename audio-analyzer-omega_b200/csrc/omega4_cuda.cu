@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -316,7 +317,7 @@ struct SparseSet {
     // windowing operand with 2 / 4 / 8 / 16 block positions per bin and 32-column aligned blocks
     bool fusable = false;
     int nkx = 0;                  // bins per frame over all resolutions of the set
-    short gB[32], gX[32], gN[32], gS[32]; // per 32-column group of the GEMM: positions per bin, first bin, bins present, frame shift
+    short gB[TC_MAX_GROUPS], gX[TC_MAX_GROUPS], gN[TC_MAX_GROUPS], gS[TC_MAX_GROUPS]; // per 32-column group of the GEMM: positions per bin, first bin, bins present, frame shift
     SparseSet() { for (int i = 0; i < OMEGA4_MAX_RES; ++i) of_res[i] = -1; }
     void release() {
         for (int i = 0; i < OMEGA4_MAX_RES; ++i) { cudaFree(sp[i].T); cudaFree(sp[i].kw); cudaFree(sp[i].tb_pos); }
@@ -535,8 +536,9 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
                             const std::vector<std::vector<int>>& lo, bool tensor, SparseSet* set) {
     const int H = d->hop;
     if ((H % (tensor ? TC_KC : BD_KC)) != 0) return OMEGA4_OK;
-    // tensor: up to four column tiles of 256 (each tile = all 512 TMEM columns as main | cross); CUDA cores: the widest tile
-    const int max_cols = tensor ? 1024 : 128;
+    // tensor: up to eight column tiles of 256 (each tile = all 512 TMEM columns as main | cross; config 5 fits its 32768,
+    // 16384 and 8192-point transforms in 256 + 512 + 1280 = 2048 columns); CUDA cores: the widest tile
+    const int max_cols = tensor ? TC_MAX_GROUPS * 32 : 128;
     // exact (time-domain) windowing for the tensor-core set: one column pair per (bin, block position), up to 64
     // hop blocks per frame (config 5: 32768 / 16384 at hop 512 take 2 x 2 x 64 + 2 x 8 x 32 = 768 columns).  The
     // cosine-sum formulation loses up to 0.03 dB on a click under the window's near-zero edge and
@@ -682,7 +684,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
     set->n_halves = (cols + TC_BN - 1) / TC_BN;
     set->qs = set->n_halves * TC_BN;
     {
-        bool ok = set->n_halves * (TC_BN / 32) <= 32;
+        bool ok = set->n_halves * (TC_BN / 32) <= TC_MAX_GROUPS;
         int xo = 0;
         for (int si = 0; si < set->n; ++si) {
             SparseRes& sp = set->sp[si];
@@ -690,7 +692,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
             sp.xoff = xo; xo += sp.nk;
         }
         set->nkx = xo;
-        for (int g = 0; g < 32; ++g) { set->gB[g] = 0; set->gX[g] = 0; set->gN[g] = 0; set->gS[g] = -1; }
+        for (int g = 0; g < TC_MAX_GROUPS; ++g) { set->gB[g] = 0; set->gX[g] = 0; set->gN[g] = 0; set->gS[g] = -1; }
         if (ok)
             for (int si = 0; si < set->n; ++si) {
                 const SparseRes& sp = set->sp[si];
@@ -1428,6 +1430,9 @@ struct StreamCtx {
     DevBuf d_in, d_out;
     double* h64 = nullptr; size_t h64_cap = 0;            // pinned staging of the meter update
     DevBuf d64;
+    std::map<unsigned, cudaGraphExec_t> graphs;           // omega4_stream_hop: one captured graph per set of ready resolutions
+    std::set<unsigned> seen;
+    void drop_graphs() { for (auto& kv : graphs) cudaGraphExecDestroy(kv.second); graphs.clear(); seen.clear(); }
     int ensure(size_t in_bytes, size_t out_bytes) {
         if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         if (in_bytes > h_in_cap) { if (h_in) cudaFreeHost(h_in); h_in = nullptr; h_in_cap = 0; CK(cudaMallocHost(&h_in, in_bytes)); h_in_cap = in_bytes; }
@@ -1441,6 +1446,7 @@ struct StreamCtx {
         return d64.ensure(bytes);
     }
     void release() {
+        drop_graphs();
         if (h_in) cudaFreeHost(h_in); if (h_out) cudaFreeHost(h_out); if (h64) cudaFreeHost(h64);
         d_in.release(); d_out.release(); d64.release();
         if (s) cudaStreamDestroy(s);
@@ -1456,16 +1462,49 @@ static void stream_ctx_release(omega4_plan* p) {
     if (it != g_stream_ctx.end()) { it->second.release(); g_stream_ctx.erase(it); }
 }
 
+// enqueue one hop's work on the context's stream: H2D of the packed frames, one FFT launch per ready resolution,
+// the combine over exactly those, D2H of the packed results
+static int stream_hop_enqueue(omega4_plan* p, StreamCtx* c, unsigned ready, bool want_comb, const size_t* in_off,
+                              const size_t* out_off, size_t in_tot, size_t out_tot, size_t comb_off) {
+    CK(cudaMemcpyAsync(c->d_in.p, c->h_in, in_tot * sizeof(float), cudaMemcpyHostToDevice, c->s));
+    CombineArgs cb;
+    memset(&cb, 0, sizeof cb);
+    for (int r = 0; r < p->n_res; ++r) {
+        cb.bins[r] = p->res[r].bins; cb.first_frame[r] = 0; cb.weight[r] = p->res[r].weight;
+        if (!(ready >> r & 1)) continue;
+        const ResInfo& ri = p->res[r];
+        MultiresArgs a;
+        memset(&a, 0, sizeof a);
+        a.x = (const float*)c->d_in.p + in_off[r]; a.ch_stride = 0; a.frame_stride = ri.n; a.frame_off0 = 0;
+        a.n_ch = 1; a.n_frames = 1; a.first_frame = 0; a.rounds = 1;
+        a.window = ri.window; a.binw = ri.binw; a.twM = ri.tw.twM; a.twN = ri.tw.twN;
+        a.mag_out = (float*)c->d_out.p + out_off[r];
+        int rc = launch_multires(ri.log2m, a, c->s);
+        if (rc) return rc;
+        cb.mag[r] = a.mag_out;
+    }
+    if (want_comb) {
+        cb.n_hops = 0; cb.n_rows = 1; cb.T = p->T;
+        cb.csr_ptr = p->csr_ptr; cb.csr_res = p->csr_res; cb.csr_lo = p->csr_lo; cb.csr_frac = p->csr_frac;
+        cb.out = (float*)c->d_out.p + comb_off;
+        combine_kernel<<<(unsigned)((p->T + 255) / 256), 256, 0, c->s>>>(cb);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(c->h_out, c->d_out.p, out_tot * sizeof(float), cudaMemcpyDeviceToHost, c->s));
+    return OMEGA4_OK;
+}
+
 extern "C" int omega4_stream_hop(omega4_plan* p, const float* const* frames, float* const* magnitudes, float* combined) {
     if (!p || !frames || !magnitudes) return fail(OMEGA4_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(p->device));
     size_t in_off[OMEGA4_MAX_RES], out_off[OMEGA4_MAX_RES], in_tot = 0, out_tot = 0;
+    unsigned ready = 0;
     int n_ready = 0;
     for (int r = 0; r < p->n_res; ++r) {
         in_off[r] = in_tot; out_off[r] = out_tot;
         if (frames[r]) {
             if (!magnitudes[r]) return fail(OMEGA4_ERR_INVALID, "a ready resolution needs a magnitude buffer");
-            in_tot += (size_t)p->res[r].n; out_tot += ((size_t)p->res[r].bins + 3) / 4 * 4; ++n_ready;
+            in_tot += (size_t)p->res[r].n; out_tot += ((size_t)p->res[r].bins + 3) / 4 * 4; ++n_ready; ready |= 1u << r;
         }
     }
     const size_t comb_off = out_tot;
@@ -1475,36 +1514,41 @@ extern "C" int omega4_stream_hop(omega4_plan* p, const float* const* frames, flo
         return OMEGA4_OK;
     }
     StreamCtx* c = stream_ctx(p);
+    const bool grew = in_tot * sizeof(float) > c->h_in_cap || out_tot * sizeof(float) > c->h_out_cap;
     int rc = c->ensure(in_tot * sizeof(float), out_tot * sizeof(float)); if (rc) return rc;
+    if (grew) c->drop_graphs();                                   // the staging buffers moved
     for (int r = 0; r < p->n_res; ++r)
         if (frames[r]) memcpy(c->h_in + in_off[r], frames[r], (size_t)p->res[r].n * sizeof(float));
-    CK(cudaMemcpyAsync(c->d_in.p, c->h_in, in_tot * sizeof(float), cudaMemcpyHostToDevice, c->s));
-    CombineArgs cb;
-    memset(&cb, 0, sizeof cb);
-    for (int r = 0; r < p->n_res; ++r) {
-        cb.bins[r] = p->res[r].bins; cb.first_frame[r] = 0; cb.weight[r] = p->res[r].weight;
-        if (!frames[r]) continue;
-        const ResInfo& ri = p->res[r];
-        MultiresArgs a;
-        memset(&a, 0, sizeof a);
-        a.x = (const float*)c->d_in.p + in_off[r]; a.ch_stride = 0; a.frame_stride = ri.n; a.frame_off0 = 0;
-        a.n_ch = 1; a.n_frames = 1; a.first_frame = 0; a.rounds = 1;
-        a.window = ri.window; a.binw = ri.binw; a.twM = ri.tw.twM; a.twN = ri.tw.twN;
-        a.mag_out = (float*)c->d_out.p + out_off[r];
-        p->launches++;
-        rc = launch_multires(ri.log2m, a, c->s);
+    // The same set of ready resolutions recurs on every hop once the rings have filled: its copies and launches are
+    // captured into a CUDA graph on the second occurrence (the first one runs eagerly and sets the kernels' attributes)
+    // and replayed with one launch afterwards.  OMEGA4_STREAM_GRAPH=0 keeps the eager path.
+    const unsigned key = ready | (combined ? 1u << 31 : 0u);
+    static const bool use_graph = !(getenv("OMEGA4_STREAM_GRAPH") && atoi(getenv("OMEGA4_STREAM_GRAPH")) == 0);
+    cudaGraphExec_t exec = nullptr;
+    if (use_graph) {
+        auto it = c->graphs.find(key);
+        if (it != c->graphs.end()) exec = it->second;
+    }
+    p->launches += n_ready + (combined ? 1 : 0);
+    if (exec) {
+        CK(cudaGraphLaunch(exec, c->s));
+    } else if (use_graph && c->seen.count(key)) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(c->s, cudaStreamCaptureModeThreadLocal));
+        rc = stream_hop_enqueue(p, c, ready, combined != nullptr, in_off, out_off, in_tot, out_tot, comb_off);
+        cudaError_t e = cudaStreamEndCapture(c->s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(OMEGA4_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(OMEGA4_ERR_CUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e));
+        c->graphs[key] = exec;
+        CK(cudaGraphLaunch(exec, c->s));
+    } else {
+        c->seen.insert(key);
+        rc = stream_hop_enqueue(p, c, ready, combined != nullptr, in_off, out_off, in_tot, out_tot, comb_off);
         if (rc) return rc;
-        cb.mag[r] = a.mag_out;
     }
-    if (combined) {
-        cb.n_hops = 0; cb.n_rows = 1; cb.T = p->T;
-        cb.csr_ptr = p->csr_ptr; cb.csr_res = p->csr_res; cb.csr_lo = p->csr_lo; cb.csr_frac = p->csr_frac;
-        cb.out = (float*)c->d_out.p + comb_off;
-        p->launches++;
-        combine_kernel<<<(unsigned)((p->T + 255) / 256), 256, 0, c->s>>>(cb);
-        CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync(c->h_out, c->d_out.p, out_tot * sizeof(float), cudaMemcpyDeviceToHost, c->s));
     CK(cudaStreamSynchronize(c->s));
     for (int r = 0; r < p->n_res; ++r)
         if (frames[r]) memcpy(magnitudes[r], c->h_out + out_off[r], (size_t)p->res[r].bins * sizeof(float));

@@ -59,7 +59,8 @@ extern "C" {
      OMEGA4_BLOCKDFT_UNFUSED=1  plan build: write the GEMM result Q and assemble frames in a separate kernel
      OMEGA4_KW_F64=1            per call: float64-state K-weighting kernel instead of the float32-state one
      OMEGA4_TENSOR=0            plan build: hop-block GEMM on the CUDA cores unless OMEGA4_FLAG_TENSOR is passed
-     OMEGA4_HOST_CHUNK_MB=n     plan build: device bytes per slot of the host-buffer pipeline (default 1024) */
+     OMEGA4_HOST_CHUNK_MB=n     plan build: device bytes per slot of the host-buffer pipeline (default 1024)
+     OMEGA4_STREAM_GRAPH=0      omega4_stream_hop: launch eagerly instead of replaying the captured CUDA graph */
 
 #define OMEGA4_FLAG_SERIAL_STATS 64               /* keep the deque-statistics kernel on the caller's stream (default: it
                                                     runs on an internal side stream underneath the FFT kernels) */

@@ -106,7 +106,8 @@ def test_multires_96k_adversarial_stream_golden(golden):
         names = _names(plan)
         if tag == "default":
             assert "blockdft_tc_gemm" in names and "blockdft_asm_32768" in names and "blockdft_asm_16384" in names, names
-            assert "multires_fft_32768" not in names and "multires_fft_16384" not in names
+            assert "blockdft_asm_8192" in names                       # 256 + 512 + 1280 = 2048 GEMM columns
+            assert not any(n in names for n in ("multires_fft_32768", "multires_fft_16384", "multires_fft_8192"))
         else:
             assert "multires_fft_32768" in names and not any(n.startswith("blockdft") for n in names)
         comb = out["combined"][0]
@@ -116,12 +117,13 @@ def test_multires_96k_adversarial_stream_golden(golden):
         # target bins 1..5 come from the 32768 / 16384 transforms (tensor cores by default)
         assert_spectrum_close_per_transform(low[:, 1:6], g["combined_low"][:, 1:6], peaks[f0:, 1:6], TOL_DB, floor_db,
                                             label=f"{tag} sparse bins")
-        # the other four resolutions (full FFT kernels in both modes).  Next to two strong pure tones the float32
-        # noise of ANY fp32 transform -- the reference's pocketfft included -- is ~1e-7 of the largest magnitude,
-        # i.e. 0.009 dB at -80 dB: the gate for this adversarial stream sits at -70 dB
+        # the other resolutions: 8192 rides the tensor-core GEMM too in the default mode (bins 6 .. 25), the rest are
+        # full FFT kernels.  Next to two strong pure tones the float32 noise of ANY fp32 transform -- the reference's
+        # pocketfft included -- is ~1e-7 of the largest magnitude, i.e. 0.009 dB at -80 dB: the FFT kernels are
+        # held to -70 dB on this adversarial stream, the tensor-core path to its -60 dB
         for k in (75, 130, 149):
-            assert_spectrum_close_per_transform(comb[k, 6:], g[f"combined_h{k}"][6:], peaks[k, 6:], TOL_DB, -70.0,
-                                                label=f"{tag} hop {k}")
+            assert_spectrum_close_per_transform(comb[k, 6:], g[f"combined_h{k}"][6:], peaks[k, 6:], TOL_DB,
+                                                max(floor_db, -70.0), label=f"{tag} hop {k}")
         assert np.all(comb[:63, 1] == 0) and comb[63, 1] > 0           # 32768 / 512 - 1: first filled hop
     scale = got["fft"].max(axis=1, keepdims=True) + 1e-20
     assert (np.abs(got["fft"] - got["default"]) / scale).max() < 1e-4
@@ -169,7 +171,10 @@ def test_exact_windowing_edge_shapes_at_64_blocks(golden):
     scale = full.max(axis=2, keepdims=True) + 1e-20
     assert np.array_equal(tiled == 0, one == 0)
     assert (np.abs(tiled - one) / scale).max() < 2e-6              # same kernels, different tile cuts: fp32 summation order only
-    assert (np.abs(one - full) / scale).max() < 1e-4               # against the full FFT: the tensor-core path's error floor
+    # against the full FFT: the tensor-core path's error floor is a few 1e-6 of the TRANSFORM's largest magnitude; rows
+    # whose own maximum lies 90 dB below it (the reversed stream starts with the full-scale tone while the two longest
+    # transforms have not filled yet) are therefore measured against the channel's largest value
+    assert (np.abs(one - full) / full.max(axis=(1, 2), keepdims=True)).max() < 2e-5
     plan.close()
 
 
