@@ -453,3 +453,27 @@ def test_streaming_shims_one_round_trip(golden):
         assert c4.shape == (256,)
         mr._combine_bins = 512
     plan.close()
+
+
+def test_streaming_shim_at_96k_six_resolutions(golden):
+    """MultiResolutionFFT(96000) with the six config-5 resolutions fed hop by hop (omega4_stream_hop, including the
+    32768-point kernel and the CUDA-graph replay once every ring has filled) against the reference's rows."""
+    from omega4_b200.audio.multi_resolution_fft import MultiResolutionFFT, FFTConfig
+    g = golden("multires_96k.npz")
+    x = g["x"]
+    mr = MultiResolutionFFT(96000)
+    mr.configs = [FFTConfig(tuple(r), int(n), int(h), float(w)) for r, n, h, w in
+                  zip(g["cfg_ranges"], g["cfg_sizes"], g["cfg_hops"], g["cfg_weights"])]
+    mr._setup_windows(); mr._setup_buffers(); mr._setup_frequency_arrays(); mr._setup_working_arrays()
+    n_hops = len(x) // HOP
+    for k in range(n_hops):
+        res = mr.process_audio_chunk(x[k * HOP:(k + 1) * HOP])
+        assert sorted(res) == [i for i in range(6) if g["present"][k, i]], k
+        if k >= 60:
+            comb, freqs = mr.combine_results_optimized(res, target_bins=512)
+            assert_spectrum_close(comb, g["combined_tail"][k - 60], TOL_DB, label=f"96k shim hop {k}")
+        if k == 79:
+            for i in range(6):
+                assert_spectrum_close(res[i].magnitude, g[f"mag_h79_r{i}"], TOL_DB, label=f"96k shim r{i}")
+                assert res[i].magnitude.dtype == np.float32 and len(res[i].frequencies) == len(res[i].magnitude)
+    mr.cleanup()
