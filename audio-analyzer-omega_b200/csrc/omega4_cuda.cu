@@ -192,7 +192,9 @@ static int launch_kweight32(const Kweight32Args& a, cudaStream_t s) {
 
 static int launch_stats(const StatsArgs& a, cudaStream_t s) {
     if (a.n_ch <= 0) return OMEGA4_OK;
-    if (a.fresh) {                                   // no carried state to sort: 14.7 KB per channel, 15 channels per SM
+    if (!a.fresh && a.n_frames == 1 && a.first_frame == 0 && !getenv("OMEGA4_STATS_WALK")) {
+        stats_push1_kernel<<<a.n_ch, ST_P1_THREADS, 0, s>>>(a);       // one frame on carried state: block-wide sort
+    } else if (a.fresh) {                            // no carried state to sort: 14.7 KB per channel, 15 channels per SM
         const size_t smem = stats_smem_bytes<false>();
         CK(cudaFuncSetAttribute(stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stats_kernel<false><<<a.n_ch, ST_THREADS, smem, s>>>(a);

@@ -316,6 +316,85 @@ stats_kernel(const __grid_constant__ StatsArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One frame per call on carried state (the streaming shim: ProfessionalMetering.calculate_lufs once per application
+// frame).  The walking kernel above would rebuild the sorted gated window with ONE warp (a 4096-element bitonic
+// network, ~0.3 ms) to push a single value; here a 256-thread CTA per channel sorts the gated values of the new window
+// with block-wide steps (sort size = next power of two above the window length) and evaluates the statistics directly.
+// The per-frame values are rounded to float32 and summed in double exactly as above (those sums are exact, so the
+// order does not matter): the outputs are bit-identical to the walking kernel's.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_P1_THREADS = 256;
+
+__global__ void __launch_bounds__(ST_P1_THREADS)
+stats_push1_kernel(const __grid_constant__ StatsArgs a) {
+    __shared__ float win[ST_I];                              // the new window, oldest first
+    __shared__ float srt[ST_SORT];
+    __shared__ float pk[ST_P];
+    __shared__ double red_d[ST_P1_THREADS / 32];
+    __shared__ int red_i[ST_P1_THREADS / 32];
+    const int ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* st = a.state + (size_t)ch * ST_STATE;
+    const float gate = (float)a.gate;
+    const int n0 = min(max((int)st[0], 0), ST_I), p0 = min(max((int)st[1], 0), ST_P);
+    const float nv = (float)a.lufs[ch], ntp = (float)a.tp[ch];
+    const int drop = (n0 == ST_I) ? 1 : 0, n = n0 - drop + 1;   // window after the push
+    for (int i = tid; i < n - 1; i += ST_P1_THREADS) win[i] = (float)st[8 + i + drop];
+    const int pdrop = (p0 == ST_P) ? 1 : 0, np = p0 - pdrop + 1;
+    for (int i = tid; i < np - 1; i += ST_P1_THREADS) pk[i] = (float)st[8 + ST_I + i + pdrop];
+    if (tid == 0) { win[n - 1] = nv; pk[np - 1] = ntp; }
+    __syncthreads();
+    int nsort = 32;
+    while (nsort < n) nsort <<= 1;
+    int c = 0;
+    double si = 0.0;
+    for (int i = tid; i < nsort; i += ST_P1_THREADS) {
+        const float v = (i < n) ? win[i] : CUDART_INF_F;
+        const bool g = v > gate && i < n;
+        srt[i] = g ? v : CUDART_INF_F;                        // non-gated entries sort to the end
+        if (g) { ++c; si += (double)v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+    if (lane == 0) { red_i[warp] = c; red_d[warp] = si; }
+    __syncthreads();
+    for (int k = 2; k <= nsort; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < nsort; i += ST_P1_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float x = srt[i], y = srt[l];
+                    if ((x > y) == ((i & k) == 0)) { srt[i] = y; srt[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    // new state: window and peak ring (every old value was copied to shared memory above)
+    for (int i = tid; i < n; i += ST_P1_THREADS) st[8 + i] = (double)win[i];
+    for (int i = tid; i < np; i += ST_P1_THREADS) st[8 + ST_I + i] = (double)pk[i];
+    if (tid == 0) {
+        int ns = 0;
+        double sum_i = 0.0;
+        for (int w = 0; w < ST_P1_THREADS / 32; ++w) { ns += red_i[w]; sum_i += red_d[w]; }
+        const int cm = n < ST_M ? n : ST_M, cs = n < ST_S ? n : ST_S;
+        double sum_m = 0.0, sum_s = 0.0;
+        for (int i = n - cm; i < n; ++i) sum_m += (double)win[i];
+        for (int i = n - cs; i < n; ++i) sum_s += (double)win[i];
+        float m = -CUDART_INF_F;
+        for (int i = 0; i < np; ++i) m = fmaxf(m, pk[i]);
+        double cur[5];
+        cur[0] = sum_m * (1.0 / (double)cm);
+        cur[1] = sum_s * (1.0 / (double)cs);
+        cur[2] = ns > 0 ? sum_i * (1.0 / (double)ns) : -100.0;
+        cur[3] = ns > 0 ? st_percentile_f(srt, ns, 0.95) - st_percentile_f(srt, ns, 0.10) : 0.0;
+        cur[4] = (double)m;
+        float* orow = a.out + (size_t)ch * 5;
+        for (int i = 0; i < 5; ++i) { orow[i] = (float)cur[i]; st[2 + i] = cur[i]; }
+        st[0] = (double)n; st[1] = (double)np; st[7] = 1.0;
+    }
+}
+
 template <bool CARRIED>
 inline size_t stats_smem_bytes() { return (size_t)stw_smem<CARRIED>(); }
 

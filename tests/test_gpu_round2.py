@@ -477,3 +477,42 @@ def test_streaming_shim_at_96k_six_resolutions(golden):
                 assert_spectrum_close(res[i].magnitude, g[f"mag_h79_r{i}"], TOL_DB, label=f"96k shim r{i}")
                 assert res[i].magnitude.dtype == np.float32 and len(res[i].frequencies) == len(res[i].magnitude)
     mr.cleanup()
+
+
+def test_single_frame_statistics_equal_the_walking_kernel(plan48, golden):
+    """One frame per call on carried state (stats_push1_kernel, what calculate_lufs runs per application frame) ==
+    the whole series in one call (stats_kernel), bit for bit, through window saturation (3600) and gate straddling;
+    and through omega4_meter_update on real frames."""
+    from omega4_b200 import _native as N
+    g = golden("meters_stats.npz")
+    li, tp = g["lufs_inst"], g["tp_db"]
+    one = plan48.meter_stats_host(li, tp, fresh=True)[0]
+    np.testing.assert_allclose(one, g["meters"], rtol=0, atol=TOL_LU)
+    state = np.zeros((1, N.METER_STATE_DOUBLES))
+    rows = np.empty_like(one)
+    for k in range(len(li)):
+        rows[k] = plan48.meter_stats_host(li[k:k + 1], tp[k:k + 1], state=state, fresh=(k == 0))[0, 0]
+    assert np.array_equal(rows, one)
+    assert int(state[0, 0]) == 3600 and int(state[0, 1]) == 60
+    # mixed: a tile, single frames, a tile
+    state = np.zeros((1, N.METER_STATE_DOUBLES))
+    parts = [plan48.meter_stats_host(li[:3590], tp[:3590], state=state, fresh=True)[0]]
+    for k in range(3590, 3620):
+        parts.append(plan48.meter_stats_host(li[k:k + 1], tp[k:k + 1], state=state)[0])
+    parts.append(plan48.meter_stats_host(li[3620:], tp[3620:], state=state)[0])
+    assert np.array_equal(np.concatenate(parts), one)
+    # omega4_meter_update on explicit frames == omega4_meter_frames + omega4_meter_stats
+    gm = golden("meters_stream.npz")
+    x = gm["x"]
+    frames = np.stack([x[(k + 1) * HOP - W:(k + 1) * HOP] * np.hanning(W) for k in range(3, 60)])
+    l2, t2, _ = plan48.meter_frames_host(frames)
+    want = plan48.meter_stats_host(l2, t2, fresh=True)[0]
+    st = np.zeros(N.METER_STATE_DOUBLES)
+    out = np.zeros(5, np.float32)
+    for k, fr in enumerate(frames):
+        fr = np.ascontiguousarray(fr)
+        N.check(N.lib().omega4_meter_update(plan48.handle, fr.ctypes.data, st.ctypes.data, 1 if k == 0 else 0, out.ctypes.data, None, None),
+                "omega4_meter_update")
+        # the true-peak kernel packs two frames per transform: a frame measured alone and the same frame packed with
+        # its neighbour differ in the last float32 digit; the loudness columns do not depend on the pairing
+        assert np.array_equal(out[:4], want[k, :4]) and abs(out[4] - want[k, 4]) <= 1e-5, k
