@@ -235,7 +235,11 @@ kweight32_kernel(const __grid_constant__ Kweight32Args a) {
         double ms = 0.0;
         if (!gated) {                                                    // warp-uniform
             // section loop not unrolled: one forward and one backward body serve both sections
+#ifdef KW32_UNROLL_SECTIONS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int si = 0; si < 2; ++si) {
                 const Kw32Sec& c = a.s[si];
                 kw32_odd_pad(r, lane);

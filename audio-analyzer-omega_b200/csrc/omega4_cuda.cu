@@ -314,6 +314,7 @@ struct SparseSet {
     int cols = 0, qs = 0;         // used GEMM columns, Q row stride (padded columns)
     float* E = nullptr;           // CUDA-core GEMM operand [hop][qs]            (blockdft_kernel.cuh)
     uint8_t* Eimg = nullptr;      // tensor-core operand images, hi/lo, swizzled  (blockdft_tc_kernel.cuh)
+    float e_inv = 1.f;            // inverse of the images' power-of-two scale (half operands)
     int n_halves = 0;
     // fused frame assembly in the GEMM epilogue: possible when every resolution of the set uses the exact-
     // windowing operand with 2 / 4 / 8 / 16 block positions per bin and 32-column aligned blocks
@@ -719,6 +720,15 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
     }
     const int nkc = H / TC_KC;
     std::vector<uint8_t> img((size_t)set->n_halves * nkc * 2 * TC_B_BYTES, 0);
+#if TC_F16
+    // one power-of-two scale for the whole table: its largest entry lands in [0.5, 1) of half's range
+    float emax = 0.f;
+    for (const auto& ec : ecols) for (float v : ec) emax = fmaxf(emax, fabsf(v));
+    int eexp = 0;
+    if (emax > 0.f) frexpf(emax, &eexp);                   // emax = [0.5, 1) 2^eexp
+    const float escale = ldexpf(1.f, -eexp);
+    set->e_inv = ldexpf(1.f, eexp);
+#endif
     for (int si = 0; si < set->n; ++si) {
         const SparseRes& sp = set->sp[si];
         const int rc_cols = 2 * sp.nk * sp.nt;
@@ -726,6 +736,16 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
             const int col = sp.col0 + cc, h = col / TC_BN, n = col % TC_BN;
             for (int k = 0; k < H; ++k) {
                 const float v = ecols[si][(size_t)k * rc_cols + cc];
+#if TC_F16
+                const float vs = v * escale;
+                const __half hh = __float2half_rn(vs);
+                const __half hl = __float2half_rn((vs - __half2float(hh)) * TC_LO_SCALE);
+                const int kc = k / TC_KC, e = k % TC_KC;
+                const size_t base = ((size_t)(h * nkc + kc) * 2) * TC_B_BYTES;
+                const int off = tc_sw64_offset(n, e >> 3) + (e & 7) * 2;
+                memcpy(&img[base + off], &hh, 2);
+                memcpy(&img[base + TC_B_BYTES + off], &hl, 2);
+#else
                 uint32_t bits; memcpy(&bits, &v, 4); bits &= 0xFFFFE000u;
                 float hi; memcpy(&hi, &bits, 4);
                 const float lo2 = v - hi;
@@ -734,6 +754,7 @@ static int build_sparse_set(omega4_plan* p, const omega4_plan_desc* d, const std
                 const int off = tc_sw64_offset(n, e >> 2) + (e & 3) * 4;
                 memcpy(&img[base + off], &hi, 4);
                 memcpy(&img[base + TC_B_BYTES + off], &lo2, 4);
+#endif
             }
         }
     }
@@ -1114,14 +1135,28 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         if (nb > 0) {
             const size_t qbytes = fusedx ? (size_t)n_ch * set.nkx * n_hops * sizeof(float2)
                                          : (size_t)n_ch * nb * set.qs * sizeof(float);
-            int rc = qbuf->ensure(qbytes);
+            const size_t qoff_scale = (qbytes + 255) & ~(size_t)255;           // [n_ch][nb] row scales behind Q / X
+            int rc = qbuf->ensure(qoff_scale + (tensor ? (size_t)n_ch * nb * sizeof(float) : 0));
             if (rc) return rc;
+            (void)qoff_scale;
             Q = (float*)qbuf->p;
             if (tensor) {
                 BlockDftTcArgs g;
                 memset(&g, 0, sizeof g);
                 g.x = x; g.ch_stride = ch_stride; g.hop = p->hop; g.n_ch = n_ch; g.j0 = j0; g.nb = nb;
                 g.n_halves = set.n_halves; g.Eimg = set.Eimg; g.Q = (float*)qbuf->p; g.qs = set.qs;
+#if TC_F16
+                {   // per hop-block row operand scale (half's exponent range is spent below each row's own maximum)
+                    HopScaleArgs h;
+                    h.x = x; h.ch_stride = ch_stride; h.hop = p->hop; h.n_ch = n_ch; h.j0 = j0; h.nb = nb;
+                    h.inv = (float*)((char*)qbuf->p + qoff_scale);
+                    g.row_inv = h.inv; g.e_inv = set.e_inv;
+                    const long long rows = (long long)n_ch * nb;
+                    Bracket b(p, s, timing, "blockdft_row_scale");
+                    hopblock_scale_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h);
+                    CK(cudaGetLastError());
+                }
+#endif
                 if (fusedx) {
                     g.X = (float2*)qbuf->p; g.n_frames = n_hops; g.nkx = set.nkx;
                     memcpy(g.gB, set.gB, sizeof g.gB); memcpy(g.gX, set.gX, sizeof g.gX); memcpy(g.gN, set.gN, sizeof g.gN);
@@ -1130,11 +1165,35 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 }
                 const size_t smem = blockdft_tc_smem_bytes();
                 CK(cudaFuncSetAttribute(blockdft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                const long long grid = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
-                if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
+                const long long n_tiles = (long long)((nb + TC_BM - 1) / TC_BM) * n_ch * set.n_halves;
+                if (n_tiles > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "blockdft grid too large");
+                g.n_tiles = (int)n_tiles;
+                // persistent: one CTA per SM walks over the tiles (b, b + grid, ...; the column tiles of a row tile run
+                // side by side on neighbouring SMs, so the samples are read from HBM once)
+                static int n_sm = 0;
+                if (!n_sm) { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+                const bool persistent = !getenv("OMEGA4_TC_ONE_TILE_PER_CTA");
+                const long long grid = persistent ? std::min<long long>(n_tiles, n_sm) : n_tiles;
                 Bracket b(p, s, timing, "blockdft_tc_gemm");
-                blockdft_tc_kernel<<<(unsigned)grid, TC_THREADS + 64, smem, s>>>(g);
+                blockdft_tc_kernel<<<(unsigned)grid, TC_CTA_THREADS, smem, s>>>(g);
                 CK(cudaGetLastError());
+#ifdef TC_TIMELINE
+                {   // developer builds: phase durations (cycles) of the second tile of every 4th CTA, median over the sampled CTAs
+                    static long long h[64][16];
+                    CK(cudaStreamSynchronize(s));
+                    CK(cudaMemcpyFromSymbol(h, tc_tl, sizeof h));
+                    const int n = (int)std::min<long long>(64, (grid + 3) / 4);
+                    const char* nm[12] = {"wait_empty+operands", "mma_issue_loop", "commit->full_seen", "tmem_drain", "epilogue_rest", "tile_period",
+                                          "cg2 wait::ld", "cg2 acc+sts", "cg2 ld issue", "cg2 bar1", "cg2 sums", "cg2 bar2"};
+                    const int from[12] = {0, 1, 2, 3, 4, 0, 8, 9, 10, 11, 12, 13}, to[12] = {1, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14};
+                    for (int k = 0; k < 12; ++k) {
+                        std::vector<long long> d;
+                        for (int i = 0; i < n; ++i) d.push_back(h[i][to[k]] - h[i][from[k]]);
+                        std::sort(d.begin(), d.end());
+                        fprintf(stderr, "tc_timeline %-20s median %lld  p10 %lld  p90 %lld\n", nm[k], d[n / 2], d[n / 10], d[n * 9 / 10]);
+                    }
+                }
+#endif
             } else {
                 BlockDftGemmArgs g;
                 memset(&g, 0, sizeof g);

@@ -41,7 +41,7 @@ SR, HOP, T_BINS, CHANNELS = 48000, 512, 512, 2
 B_ALG_PER_HOP = 2048 + 2048 + 20          # SURVEY.md section 8d, fused-output mode: 512 f32 in, 512 f32 + 5 f32 out
 FLOP_PER_HOP = 0.9e6                      # SURVEY.md section 8d nominal estimate (all four FFTs + meters on CUDA cores)
 FLOP_TENSOR_FFT = 266240 + 122880         # the 8192 + 4096 FFTs of that estimate: now a tensor-core GEMM instead
-TENSOR_FLOP_PER_HOP = 3 * 2 * 960 * 512   # 3xTF32 hop-block GEMM: 960 columns x 512 samples per hop block
+TENSOR_FLOP_PER_HOP = 3 * 2 * 960 * 512   # split-precision hop-block GEMM (three products): 960 columns x 512 samples per hop block
 FP32_PEAK_TFLOPS = 70.8                   # measured FFMA peak on this pool's B200 (profiles/r01_fp_pipes_microbench.txt:
                                           # 121.7 lanes/clk/SM x 148 SMs x 1.965 GHz x 2); nominal 75
 
@@ -584,7 +584,7 @@ def main():
             out_bytes = {"multires_fft_8192": 6 * 4, "multires_fft_4096": 20 * 4, "multires_fft_2048": 102 * 4,
                          "multires_fft_1024": 384 * 4, "true_peak": 8, "kweight_lufs": 8, "meter_stats": 20,
                          "blockdft_gemm": 128 * 4, "blockdft_tc_gemm": 50 * 8, "blockdft_asm_8192": 6 * 4,
-                         "blockdft_asm_4096": 20 * 4}.get(dom, 0)
+                         "blockdft_asm_4096": 20 * 4, "blockdft_row_scale": 4}.get(dom, 0)
             if dom.startswith("multires_fft_") and not is48_wl:      # config5: target bins per resolution differ
                 out_bytes = {"multires_fft_4096": 102 * 4, "multires_fft_2048": 179 * 4, "multires_fft_1024": 205 * 4}.get(dom, out_bytes)
             in_bytes = {"meter_stats": 16, "blockdft_asm_8192": 100 * 4, "blockdft_asm_4096": 400 * 4}.get(dom, HOP * 4)
@@ -621,7 +621,7 @@ def main():
             "metric": METRIC if is48 else METRIC.replace("48 kHz stereo", "96 kHz 8-channel"),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f32 (FFT, combine, true peak, K-weighting in a float32 delta-form state; 3xTF32 tensor-core GEMM for the few-bin resolutions) + f64 (meter statistics)",
+            "dtype": "f32 (FFT, combine, true peak, K-weighting in a float32 delta-form state; tensor-core GEMM on (hi, lo) half operands with fp32 accumulators for the few-bin resolutions) + f64 (meter statistics)",
             "data": "synthetic",
             "config": {"workload": f"{wl_name}: {n_streams} streams x {CHANNELS} ch x {seconds} s @{SR // 1000} kHz per GPU"
                                    + (f" ({n_streams * world} streams in total, strong scaling)" if scaling == "strong" else "")
@@ -646,7 +646,7 @@ def main():
                 "executed_cuda_cores": {"flop_per_channel_hop": FLOP_PER_HOP - FLOP_TENSOR_FFT, "achieved_tflops": executed,
                                         "frac": executed / FP32_PEAK_TFLOPS,
                                         "note": "without the 8192 + 4096 FFTs, whose bins come from the tensor-core GEMM"},
-                "tensor_cores": {"flop_per_channel_hop": TENSOR_FLOP_PER_HOP, "kind": "tf32 (3xTF32 split)",
+                "tensor_cores": {"flop_per_channel_hop": TENSOR_FLOP_PER_HOP, "kind": "f16 (hi + lo / 2^11 split of row-scaled operands, three products, fp32 accumulators)",
                                  "achieved_tflops_in_kernel": (k_hops * TENSOR_FLOP_PER_HOP / (ktimes["blockdft_tc_gemm"] / 1e3) / 1e12)
                                  if ktimes.get("blockdft_tc_gemm") else None},
                 "peak_tflops_measured": FP32_PEAK_TFLOPS,
