@@ -25,6 +25,7 @@
 #include "multires_kernel.cuh"
 #include "stats_kernel.cuh"
 #include "truepeak_kernel.cuh"
+#include "truepeak16_kernel.cuh"
 #include "waterfall_kernel.cuh"
 
 using namespace o4;
@@ -156,6 +157,21 @@ static int launch_truepeak(const TruePeakArgs& a, cudaStream_t s) {
     if (grid <= 0) return OMEGA4_OK;
     if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "truepeak grid too large");
     truepeak_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return OMEGA4_OK;
+}
+
+static int launch_truepeak16(const TruePeakArgs& a, cudaStream_t s) {
+    constexpr int L = 11;
+    using S = FftShape<L>;
+    const size_t smem = truepeak16_smem_bytes<L>();
+    CK(cudaFuncSetAttribute(truepeak16_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ppc = a.rounds * S::CONC;                    // frame pairs per CTA
+    const int n_pairs = (a.n_frames + 1) / 2;
+    const long long grid = (long long)((n_pairs + ppc - 1) / ppc) * a.n_ch;
+    if (grid <= 0) return OMEGA4_OK;
+    if (grid > 2147483647LL) return fail(OMEGA4_ERR_INVALID, "truepeak grid too large");
+    truepeak16_kernel<L><<<(unsigned)grid, S::NT, smem, s>>>(a);
     CK(cudaGetLastError());
     return OMEGA4_OK;
 }
@@ -1056,7 +1072,8 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             fill_truepeak_steps(&t);
             t.tp_out = tp;
             Bracket b(p, s, timing, "true_peak");
-            int rc = launch_truepeak(t, s);
+            const bool exact_tp = (flags & OMEGA4_FLAG_EXACT_TRUE_PEAK) || getenv("OMEGA4_TP_F32");
+            int rc = exact_tp ? launch_truepeak(t, s) : launch_truepeak16(t, s);
             if (rc) return rc;
         }
         if (meters) {

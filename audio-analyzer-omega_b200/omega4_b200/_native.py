@@ -31,6 +31,7 @@ FLAG_NO_TENSOR = 16
 FLAG_TENSOR = 32
 FLAG_SERIAL_STATS = 64
 FLAG_FRESH_BARS = 128
+FLAG_EXACT_TRUE_PEAK = 256
 ABI_VERSION = 2
 WATERFALL_STATE = 41
 

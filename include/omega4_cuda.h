@@ -60,12 +60,19 @@ extern "C" {
      OMEGA4_KW_F64=1            per call: float64-state K-weighting kernel instead of the float32-state one
      OMEGA4_TENSOR=0            plan build: hop-block GEMM on the CUDA cores unless OMEGA4_FLAG_TENSOR is passed
      OMEGA4_HOST_CHUNK_MB=n     plan build: device bytes per slot of the host-buffer pipeline (default 1024)
-     OMEGA4_STREAM_GRAPH=0      omega4_stream_hop: launch eagerly instead of replaying the captured CUDA graph */
+     OMEGA4_STREAM_GRAPH=0      omega4_stream_hop: launch eagerly instead of replaying the captured CUDA graph
+     OMEGA4_TP_F32=1            per call: float32 true-peak kernel for the batch path too (see OMEGA4_FLAG_EXACT_TRUE_PEAK)
+     OMEGA4_TC_ONE_TILE_PER_CTA=1  per call: hop-block GEMM with one tile per CTA instead of the persistent walk */
 
 #define OMEGA4_FLAG_SERIAL_STATS 64               /* keep the deque-statistics kernel on the caller's stream (default: it
                                                     runs on an internal side stream underneath the FFT kernels) */
 
 #define OMEGA4_FLAG_FRESH_BARS 128                /* omega4_analyze_io: ignore bars_state contents on entry */
+
+#define OMEGA4_FLAG_EXACT_TRUE_PEAK 256           /* batch entry points: evaluate the three delayed phases of the 4x true
+                                                    peak in float32 (4e-6 dBTP from the reference) instead of half precision on
+                                                    two frame pairs at a time (<= 0.02 dBTP, bar 0.05; truepeak16_kernel.cuh).
+                                                    The explicit-frame entry points always use float32. */
 
 typedef struct omega4_plan omega4_plan;
 

@@ -527,9 +527,14 @@ def test_meters_stream_golden(plan, golden):
     assert np.abs(out["tp_db"][0, f:] - g["tp_db"]).max() <= TOL_TP
     _meters_close(out["meters"][0, f:], g["meters"], "stream")
     assert np.all(out["meters"][0, :f] == [-100, -100, -100, 0, -100])
-    # much tighter than the gate in practice
+    # much tighter than the gate in practice; the batch path evaluates the delayed true-peak phases in half precision
+    # (truepeak16_kernel.cuh: ~0.01 dBTP), OMEGA4_FLAG_EXACT_TRUE_PEAK keeps them in float32
     assert np.abs(out["lufs_inst"][0, f:] - g["lufs_inst"]).max() < 1e-5
-    assert np.abs(out["tp_db"][0, f:] - g["tp_db"]).max() < 1e-3
+    assert np.abs(out["tp_db"][0, f:] - g["tp_db"]).max() < 0.03
+    from omega4_b200 import _native as N
+    ex = plan.analyze_host(g["x"][None, :], want_combined=False, want_meters=True, want_series=True, flags=N.FLAG_EXACT_TRUE_PEAK)
+    assert np.abs(ex["tp_db"][0, f:] - g["tp_db"]).max() < 1e-3
+    assert np.array_equal(ex["lufs_inst"], out["lufs_inst"])
     assert np.all(out["lufs_inst"][0, 44:46] == -100.0)               # digital silence -> rms gate
 
 
@@ -783,7 +788,8 @@ def test_batch_driver_tiles_match_one_shot_and_oracle(plan):
     # spectra and LUFS columns are bit-identical; the true-peak kernel packs two consecutive frames into
     # one complex transform, so a different tiling pairs frames differently: same value to fp32 rounding
     assert k == n_hops and torch.equal(comb_t, comb) and torch.equal(met_t[..., :4], met[..., :4])
-    assert float((met_t[..., 4] - met[..., 4]).abs().max()) < 1e-4
+    # (half-precision delayed phases on the batch path: two evaluations of a frame in different lanes agree to ~0.01 dBTP)
+    assert float((met_t[..., 4] - met[..., 4]).abs().max()) < 0.03
     # channels are independent: a single channel run alone gives the same rows
     solo = plan.analyze_host(x[4:5])
     assert np.array_equal(solo["combined"][0], host["combined"][4]) and np.array_equal(solo["meters"][0], host["meters"][4])

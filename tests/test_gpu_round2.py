@@ -48,7 +48,11 @@ def test_meters_96k_eight_channels_golden(golden):
         worst[tag] = (dl, dt)
     assert np.array_equal(out["meters"], o["meters"])                # the decode is exact: bit-identical rows
     # in practice far inside the gate, also with alpha four times smaller than at 48 kHz
-    assert worst["s16"][0] < 1e-4 and worst["s16"][1] < 1e-3, worst
+    # (true peak: half-precision delayed phases on the batch path, ~0.01 dBTP; float32 with OMEGA4_FLAG_EXACT_TRUE_PEAK)
+    assert worst["s16"][0] < 1e-4 and worst["s16"][1] < 0.03, worst
+    from omega4_b200 import _native as N
+    ex = plan.analyze_host(x16.astype(np.float32) / 32768.0, want_combined=False, want_series=True, flags=N.FLAG_EXACT_TRUE_PEAK)
+    assert np.abs(ex["tp_db"][:, f:] - g["tp_db"]).max() < 1e-3
     assert np.all(out["lufs_inst"][1, 23:30] == -100.0)              # digital silence -> rms gate
     assert np.all(out["meters"][4, :, 2] == -100.0)                  # a few LSB never pass the -70 gate
     os.environ["OMEGA4_KW_F64"] = "1"
