@@ -445,6 +445,7 @@ struct omega4_plan {
     double kw_gain = 1.0;
     Twiddles tw_meter;            // W-point complex transform of the true-peak kernel
     float2* tp_rot = nullptr;     // [3][W] fractional-delay factors
+    unsigned* tp_rot_h = nullptr; // the same as packed half (re, im) for the all-half kernel
     SparseSet set_cc;             // fp32 CUDA-core GEMM: up to 128 columns
     SparseSet set_tc;             // 3xTF32 tcgen05 GEMM: up to 512 columns
     bool tensor_default = true;   // OMEGA4_TENSOR=0 makes the CUDA-core GEMM the default
@@ -875,6 +876,12 @@ static int plan_build(omega4_plan* p, const omega4_plan_desc* d) {
                 rot[(size_t)(ph - 1) * W + k] = v;
             }
         rc = upload((void**)&p->tp_rot, rot.data(), rot.size() * sizeof(float2)); if (rc) return rc;
+        std::vector<unsigned> roth(rot.size());
+        for (size_t i = 0; i < rot.size(); ++i) {
+            const __half2 h = __floats2half2_rn(rot[i].x, rot[i].y);
+            memcpy(&roth[i], &h, sizeof(unsigned));
+        }
+        rc = upload((void**)&p->tp_rot_h, roth.data(), roth.size() * sizeof(unsigned)); if (rc) return rc;
     }
     return OMEGA4_OK;
 }
@@ -912,7 +919,7 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
         p->scratch_mag[r].release(); p->h_mag[r].release();
     }
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
-    cudaFree(p->hann64); cudaFree(p->hann32); cudaFree(p->tp_rot);
+    cudaFree(p->hann64); cudaFree(p->hann32); cudaFree(p->tp_rot); cudaFree(p->tp_rot_h);
     p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
     p->scratch_comb.release(); p->scratch_bstate.release();
     p->set_cc.release(); p->set_tc.release();
@@ -1068,7 +1075,7 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             t.frame_off0 = (long long)p->hop - p->W;
             t.n_ch = n_ch; t.n_frames = n_hops; t.first_frame = first_m;
             t.rounds = default_rounds((n_hops + 1) / 2, 2);
-            t.window = p->hann32; t.twM = p->tw_meter.twM; t.rot = p->tp_rot;
+            t.window = p->hann32; t.twM = p->tw_meter.twM; t.rot = p->tp_rot; t.rot_h = p->tp_rot_h;
             fill_truepeak_steps(&t);
             t.tp_out = tp;
             Bracket b(p, s, timing, "true_peak");

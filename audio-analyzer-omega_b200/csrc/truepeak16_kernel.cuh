@@ -1,20 +1,27 @@
-// truepeak16_kernel.cuh -- the batch path's 4x true peak with the three delayed phases evaluated in half precision,
-// TWO frame pairs (four frames) per transform.
+// truepeak16_kernel.cuh -- the batch path's 4x true peak with the transforms evaluated in half precision, TWO frame
+// pairs (four frames) per transform.
 //
 // Same contract, same formulation as truepeak_kernel.cuh (scipy.signal.resample(x, 4 len(x)) -> max |.| -> 20 log10,
 // omega4/panels/professional_meters.py:283-299): frames a, b packed as z = a + i b, one forward transform, then for the
 // phases p = 1, 2, 3 the "inverse" transform of Z .* R_p, of which only max |Re|, max |Im| are needed.  What changes:
-//   * phase 0 (the samples themselves, scaled to unit peak) and the forward transform stay float32;
-//   * the spectrum Z is stored as half (re, im), and the delayed phases are computed with HFMA2 / HADD2 on
-//     (pair A, pair B) half2 lanes: every butterfly instruction, every shared-memory exchange and every barrier of the
-//     three inverse transforms serves two frame pairs.  Those transforms were 3/4 of the kernel.
+//   * phase 0 (the samples themselves: the sample peak, and the scale that brings every frame to unit peak) stays
+//     float32 and exact;
+//   * the forward transform and the three delayed phases run with HFMA2 / HADD2 on (pair A, pair B) half2 lanes: every
+//     butterfly instruction, every shared-memory exchange and every barrier serves two frame pairs; the spectrum is
+//     kept as half (re, im) of both pairs in shared memory, stage twiddles and the delay factors R_p are packed half.
+// What it buys (tools/micro/f32x2_pipes.cu, profiles/r02l_f32x2_pipes.txt): HADD2 / HFMA2 / HMUL2 issue at 1.9 warp
+// instructions per clock and SM against 3.7 for FADD / FFMA -- a half2 instruction costs the FMA pipe two slots, so the
+// arithmetic rate per transform is the float32 one; the gain is in everything else (issue slots, shared-memory
+// wavefronts, barriers, registers): 102.6 ms (float32) -> 77.5 (delayed phases in half, r02k) -> 65 ms (all four
+// transforms, r02l) per 11.52 M frames.
 // Accuracy: a delayed phase only matters where it exceeds the sample peak, and then as a maximum of values of the
 // frame's own size; half keeps 11 significant bits through 11 butterfly levels, which leaves the peak within
-// ~2e-3 dB typically and 0.02 dB at worst of the float64 reference (north star: 0.05 dBTP; numpy emulation of this
-// arithmetic over sines, noise, clipped noise, square waves, impulses: tests/tools/truepeak16_numerics.py, on the
-// GPU: the golden / stress tests).  The float32 kernel stays the one the explicit-frame entry points
-// (omega4_meter_frames, the streaming shim's calculate_true_peak) run, and OMEGA4_FLAG_EXACT_TRUE_PEAK /
-// OMEGA4_TP_F32=1 select it for the batch path as well.
+// ~2e-3 dB typically and 0.023 dB at worst of the float64 reference (north star: 0.05 dBTP; numpy emulation of this
+// arithmetic over sines, noise, clipped noise, square waves, impulses, random walks: tests/tools/truepeak16_numerics.py
+// -- the forward transform's rounding adds little to what the three inverse transforms carry: max 0.023 instead of
+// 0.022, p99 0.013 / 0.011 over 600 frames; on the GPU: the golden / stress tests, <= 0.016).  The float32 kernel
+// stays the one the explicit-frame entry points (omega4_meter_frames, the streaming shim's calculate_true_peak) run,
+// and OMEGA4_FLAG_EXACT_TRUE_PEAK / OMEGA4_TP_F32=1 select it for the batch path as well.
 #pragma once
 #include <cuda_fp16.h>
 #include "truepeak_kernel.cuh"
@@ -83,16 +90,27 @@ __device__ __forceinline__ void hbf16(c2h* v) {
 #pragma unroll
         for (int d = c + 1; d < 4; ++d) { const c2h tmp = v[4 * c + d]; v[4 * c + d] = v[4 * d + c]; v[4 * d + c] = tmp; }
 }
-__device__ __forceinline__ void h_apply_twiddles(c2h* v, const Tw15& t) {
+// stage twiddles as packed half (re, im): 15 registers per stage, no conversions in the loop
+struct TwH15 { __half2 w[15]; };
+struct LocalTwH { TwH15 s1, s2; };
+__device__ __forceinline__ void h_apply_twiddles(c2h* v, const TwH15& t) {
 #pragma unroll
-    for (int k = 1; k < 16; ++k) v[k] = hc_mul(v[k], __floats2half2_rn(t.w[k - 1].x, t.w[k - 1].y));
+    for (int k = 1; k < 16; ++k) v[k] = hc_mul(v[k], t.w[k - 1]);
+}
+template <int LOG2M>
+__device__ __forceinline__ void pack_local_twiddles(const LocalTwFull<LOG2M>& a, LocalTwH& o) {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        o.s1.w[k] = __floats2half2_rn(a.s1.w[k].x, a.s1.w[k].y);
+        o.s2.w[k] = __floats2half2_rn(a.s2.w[k].x, a.s2.w[k].y);
+    }
 }
 
 // fft_forward_local<LOG2M, true> on half2 lanes: on entry v[16] = z[t + j M/16] of both transforms, on exit the last
 // stage's outputs are in v[] (nothing is written to a Z buffer).  One group barrier inside (after the stage-1 store);
 // the caller must put another one before the next store into X.
-template <int LOG2M>
-__device__ __forceinline__ void fft_local_h2(c2h* v, c2h* X, const LocalTwFull<LOG2M>& st, int t, int g) {
+template <int LOG2M, class TW>
+__device__ __forceinline__ void fft_local_h2(c2h* v, c2h* X, const TW& st, int t, int g) {
     constexpr int M = 1 << LOG2M, TPF = M / 16, G2 = M / 256, S = 17 * G2;
     static_assert(G2 == 8, "written for 2048 complex points");
     hbf16(v);
@@ -119,54 +137,42 @@ __device__ __forceinline__ void fft_local_h2(c2h* v, c2h* X, const LocalTwFull<L
     }
 }
 
-// fft_forward_local<LOG2M, false> in float32 whose natural-order output goes to word `word` of the (pair A, pair B)
-// half spectrum Zh[zaddr(k)][2] as packed half (re, im).  Two group barriers (after the stage-1 store, after the
-// final store).
-template <int LOG2M>
-__device__ __forceinline__ void fft_forward_local_zh(float2* v, float2* X, uint32_t* Zh, int word, const LocalTwFull<LOG2M>& st,
-                                                     int t, int g, bool active) {
+// The same transform with the natural-order spectrum of both pairs written to Zc[zaddr(k)] (one c2h = 8 bytes per
+// bin).  Two group barriers (after the stage-1 store, after the final store).
+template <int LOG2M, class TW>
+__device__ __forceinline__ void fft_forward_h2_z(c2h* v, c2h* X, c2h* Zc, const TW& st, int t, int g) {
     constexpr int M = 1 << LOG2M, TPF = M / 16, G2 = M / 256, S = 17 * G2;
     static_assert(G2 == 8, "written for 2048 complex points");
-    if (active) {
-        bf16pt(v);
-        apply_twiddles(v, st.s1);
+    hbf16(v);
+    h_apply_twiddles(v, st.s1);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) X[k * S + t] = v[k];
-    }
+    for (int k = 0; k < 16; ++k) X[k * S + t] = v[k];
     group_sync<TPF>(g);
     const int q = t / G2, p = t % G2;
     const int zq = zaddr<LOG2M>(q + 16 * p);
-    if (active) {
-        float2* Xq = X + q * S;
+    c2h* Xq = X + q * S;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = Xq[p + G2 * j];
-        bf16pt(v);
-        apply_twiddles(v, st.s2);
-        __syncwarp();
+    for (int j = 0; j < 16; ++j) v[j] = Xq[p + G2 * j];
+    hbf16(v);
+    h_apply_twiddles(v, st.s2);
+    __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) Xq[17 * p + k] = v[k];
-        __syncwarp();
+    for (int k = 0; k < 16; ++k) Xq[17 * p + k] = v[k];
+    __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16 / G2; ++i) {
-            const int k = p + G2 * i;
+    for (int i = 0; i < 16 / G2; ++i) {
+        const int k = p + G2 * i;
 #pragma unroll
-            for (int pp = 0; pp < G2; ++pp) v[i * G2 + pp] = Xq[17 * pp + k];
-            bf8(v + i * 8);
+        for (int pp = 0; pp < G2; ++pp) v[i * G2 + pp] = Xq[17 * pp + k];
+        hbf8(v + i * 8);
 #pragma unroll
-            for (int pq = 0; pq < G2; ++pq) {
-                const __half2 h = __floats2half2_rn(v[i * G2 + pq].x, v[i * G2 + pq].y);
-                Zh[2 * (zq + 16 * G2 * i + 256 * pq) + word] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16 / G2; ++i)
-#pragma unroll
-            for (int pq = 0; pq < G2; ++pq) Zh[2 * (zq + 16 * G2 * i + 256 * pq) + word] = 0u;
+        for (int pq = 0; pq < G2; ++pq) Zc[zq + 16 * G2 * i + 256 * pq] = v[i * G2 + pq];
     }
     group_sync<TPF>(g);
 }
 
+// One unit = two frame pairs (four frames) per 128-thread group: sample peaks (float32, = phase 0), scale to unit
+// peak, one forward and three "inverse" half2 transforms, maxima.
 template <int LOG2M>
 __global__ void __launch_bounds__(256, 2)
 truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
@@ -181,9 +187,8 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
     const int tid = threadIdx.x;
     const int g = tid / TPF;
     const int t = tid % TPF;
-    float2* X = bufs + (size_t)g * (BUF + M);
-    c2h* Xh = reinterpret_cast<c2h*>(X);
-    uint32_t* Zh = reinterpret_cast<uint32_t*>(X + BUF);                           // [M][2] half2 (re, im) of pair A, pair B
+    c2h* Xh = reinterpret_cast<c2h*>(bufs + (size_t)g * (BUF + M));
+    c2h* Zc = Xh + BUF;                                                            // [M] spectrum of pair A, pair B
     float4* red = red_all + g * 2 * WARPS;
 
     const int pairs_per_cta = a.rounds * CONC;
@@ -192,14 +197,15 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
     const int ch = blockIdx.x / tiles_per_ch;
     const int tile = blockIdx.x % tiles_per_ch;
 
-    LocalTwFull<LOG2M> st;
+    LocalTwH st;
     {
         LocalTw<LOG2M> st4;
+        LocalTwFull<LOG2M> stf;
         load_local_twiddles<LOG2M>(st4, a.twM, t);
-        expand_local_twiddles<LOG2M>(st4, st);
+        expand_local_twiddles<LOG2M>(st4, stf);
+        pack_local_twiddles<LOG2M>(stf, st);
     }
     const float inv_m = 1.0f / (float)M;
-    // group-wide component-wise maximum of a float4; every thread of the group gets the result
     auto group_max4 = [&](float4 v, int slot) -> float4 {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -220,8 +226,7 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
     };
 
     const int zt = zaddr<LOG2M>(t);
-    const float2 rbase1 = __ldg(a.rot + t), rbase2 = __ldg(a.rot + M + t), rbase3 = __ldg(a.rot + 2 * M + t);
-    // raw samples of a pair: v[j] = (a[t + j TPF], b[t + j TPF]), windowed; returns whether any of its frames is measured
+    // windowed samples of a pair: v[j] = (a[t + j TPF], b[t + j TPF])
     auto load_pair = [&](int pi, float2 (&v)[16], bool& act_a, bool& act_b) {
         const int fa = 2 * pi, fb = fa + 1;
         act_a = (fa < a.n_frames) && (fa >= a.first_frame);
@@ -246,56 +251,42 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
         const int pa_i = tile * pairs_per_cta + (2 * u) * CONC + g;
         const int pb_i = tile * pairs_per_cta + (2 * u + 1) * CONC + g;
         const bool has_b = (2 * u + 1) < a.rounds;
-        float2 v[16];
         bool aa, ab, ba = false, bb = false;
-        // ---- pair A: sample peaks, forward transform -> Zh word 0
-        load_pair(pa_i, v, aa, ab);
         float4 pk4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { pk4.x = fmaxf(pk4.x, fabsf(v[j].x)); pk4.y = fmaxf(pk4.y, fabsf(v[j].y)); }
+        c2h h[16];
         {
-            // the group-wide maximum of pair A is needed before its transform; pair B's joins the second reduction
-            const float4 m = group_max4(pk4, 0);
-            pk4.x = m.x; pk4.y = m.y;
-            const float sa = m.x > 1e-20f ? 1.f / m.x : 0.f, sb = m.y > 1e-20f ? 1.f / m.y : 0.f;
+            float2 va[16], vb[16];
+            load_pair(pa_i, va, aa, ab);
+            if (has_b) load_pair(pb_i, vb, ba, bb);
+            else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j].x *= sa; v[j].y *= sb; }
+                for (int j = 0; j < 16; ++j) vb[j] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                pk4.x = fmaxf(pk4.x, fabsf(va[j].x)); pk4.y = fmaxf(pk4.y, fabsf(va[j].y));
+                pk4.z = fmaxf(pk4.z, fabsf(vb[j].x)); pk4.w = fmaxf(pk4.w, fabsf(vb[j].y));
+            }
+            pk4 = group_max4(pk4, 0);                   // the four sample peaks = phase 0, exact
+            const float s0 = pk4.x > 1e-20f ? 1.f / pk4.x : 0.f, s1 = pk4.y > 1e-20f ? 1.f / pk4.y : 0.f;
+            const float s2 = pk4.z > 1e-20f ? 1.f / pk4.z : 0.f, s3 = pk4.w > 1e-20f ? 1.f / pk4.w : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {              // every frame to unit peak, (A, B) on the half2 lanes
+                h[j].x = __floats2half2_rn(va[j].x * s0, vb[j].x * s2);
+                h[j].y = __floats2half2_rn(va[j].y * s1, vb[j].y * s3);
+            }
         }
-        fft_forward_local_zh<LOG2M>(v, X, Zh, 0, st, t, g, aa || ab);
-        // ---- pair B
-        if (has_b) load_pair(pb_i, v, ba, bb);
-        else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
-        }
-        {
-            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { q4.z = fmaxf(q4.z, fabsf(v[j].x)); q4.w = fmaxf(q4.w, fabsf(v[j].y)); }
-            const float4 m = group_max4(q4, 1);
-            pk4.z = m.z; pk4.w = m.w;
-            const float sa = m.z > 1e-20f ? 1.f / m.z : 0.f, sb = m.w > 1e-20f ? 1.f / m.w : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j].x *= sa; v[j].y *= sb; }
-        }
-        fft_forward_local_zh<LOG2M>(v, X, Zh, 1, st, t, g, ba || bb);
-        // ---- phases 1..3 of both pairs on half2 lanes; maxima scaled by M
         __half2 mre = __float2half2_rn(0.f), mim = mre;            // (A, B) maxima of |Re| (frames a) and |Im| (frames b)
-        if (aa || ab || ba || bb) {
+        if (aa || ab || ba || bb) {                                // group-uniform
+            fft_forward_h2_z<LOG2M>(h, Xh, Zc, st, t, g);
 #pragma unroll 1
             for (int p = 1; p <= 3; ++p) {
-                const float2 rb = (p == 1) ? rbase1 : (p == 2 ? rbase2 : rbase3);
-                c2h h[16];
+                const unsigned* rot_p = a.rot_h + (p - 1) * M + t;      // delay factors as packed half, 24 KB, L1 resident
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float2 rk = cmul(rb, a.step[p - 1][j]);
-                    if (j == 8 && t == 0) rk = make_float2(a.nyq[p - 1], 0.f);      // k = W/2
-                    const uint2 zz = *reinterpret_cast<const uint2*>(Zh + 2 * (zt + j * TPF));
-                    const __half2 za = *reinterpret_cast<const __half2*>(&zz.x), zb = *reinterpret_cast<const __half2*>(&zz.y);
-                    c2h z;
-                    z.x = __lows2half2(za, zb);
-                    z.y = __highs2half2(za, zb);
-                    const c2h s = hc_mul(z, __floats2half2_rn(rk.x, rk.y));
+                    const unsigned rku = __ldg(rot_p + j * TPF);
+                    const __half2 rkh = *reinterpret_cast<const __half2*>(&rku);
+                    const c2h s = hc_mul(Zc[zt + j * TPF], rkh);
                     h[j].x = s.x; h[j].y = __hneg2(s.y);          // conj: inverse transform by the forward kernel
                 }
                 fft_local_h2<LOG2M>(h, Xh, st, t, g);
@@ -305,7 +296,7 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
             }
         }
         const float2 fre = __half22float2(mre), fim = __half22float2(mim);
-        const float4 pko = group_max4(make_float4(fre.x, fim.x, fre.y, fim.y), 0);     // (A.a, A.b, B.a, B.b)
+        const float4 pko = group_max4(make_float4(fre.x, fim.x, fre.y, fim.y), 1);     // (A.a, A.b, B.a, B.b)
         if (t == 0) {
             const float pk[4] = {pk4.x, pk4.y, pk4.z, pk4.w};
             const float po[4] = {pko.x, pko.y, pko.z, pko.w};
@@ -318,7 +309,7 @@ truepeak16_kernel(const __grid_constant__ TruePeakArgs a) {
                 a.tp_out[(size_t)ch * a.n_frames + fr[i]] = (peak < 1e-10) ? -100.0 : 20.0 * log10(peak);
             }
         }
-        group_sync<TPF>(g);          // red[] and Zh are reused by the next unit
+        group_sync<TPF>(g);          // red[] and Zc are reused by the next unit
     }
 }
 

@@ -37,6 +37,7 @@ struct TruePeakArgs {
     const float* window;       // [W] float32 Hann (hop mode) or nullptr
     const float2* twM;         // [W]      exp(-2 pi i e / W)
     const float2* rot;         // [3][W]   R_p[k], p = 1..3 (see above)
+    const unsigned* rot_h;     // [3][W]   the same as packed half (re, im); truepeak16h_kernel only
     double* tp_out;            // [n_ch][n_frames] dBTP
     // R_p[t + j W/16] = R_p[t] * step[p-1][j]:  step = e^{+2 pi i p j'/64}, j' = j (j < 8) or j - 16 (signed frequency);
     // uniform constant-bank operands instead of 48 table loads per thread and pair

@@ -621,7 +621,7 @@ def main():
             "metric": METRIC if is48 else METRIC.replace("48 kHz stereo", "96 kHz 8-channel"),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f32 (FFT, combine, K-weighting in a float32 delta-form state, true peak: samples + forward transform; its three delayed phases in f16x2; tensor-core GEMM on (hi, lo) half operands with fp32 accumulators for the few-bin resolutions) + f64 (meter statistics)",
+            "dtype": "f32 (FFT, combine, K-weighting in a float32 delta-form state, sample peaks of the true-peak meter; its four transforms per frame pair in f16x2; tensor-core GEMM on (hi, lo) half operands with fp32 accumulators for the few-bin resolutions) + f64 (meter statistics)",
             "data": "synthetic",
             "config": {"workload": f"{wl_name}: {n_streams} streams x {CHANNELS} ch x {seconds} s @{SR // 1000} kHz per GPU"
                                    + (f" ({n_streams * world} streams in total, strong scaling)" if scaling == "strong" else "")

@@ -69,9 +69,9 @@ extern "C" {
 
 #define OMEGA4_FLAG_FRESH_BARS 128                /* omega4_analyze_io: ignore bars_state contents on entry */
 
-#define OMEGA4_FLAG_EXACT_TRUE_PEAK 256           /* batch entry points: evaluate the three delayed phases of the 4x true
-                                                    peak in float32 (4e-6 dBTP from the reference) instead of half precision on
-                                                    two frame pairs at a time (<= 0.02 dBTP, bar 0.05; truepeak16_kernel.cuh).
+#define OMEGA4_FLAG_EXACT_TRUE_PEAK 256           /* batch entry points: evaluate the transforms of the 4x true peak in
+                                                    float32 (4e-6 dBTP from the reference) instead of half precision on
+                                                    two frame pairs at a time (<= 0.025 dBTP, bar 0.05; truepeak16_kernel.cuh).
                                                     The explicit-frame entry points always use float32. */
 
 typedef struct omega4_plan omega4_plan;

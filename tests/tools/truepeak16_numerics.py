@@ -1,7 +1,8 @@
-"""numpy emulation of truepeak16_kernel.cuh's arithmetic: float32 forward transform of a frame pair scaled to unit peak,
-spectrum and delay factors rounded to half, the three delayed phases by an FFT whose every operation is rounded to
+"""numpy emulation of truepeak16_kernel.cuh's arithmetic: a frame pair scaled to unit peak (float32) and rounded to
+half, forward transform, delay factors and the three delayed phases by an FFT whose every operation is rounded to
 half (radix-2 here, the kernel's radix 16 / 16 / 8 has the same 11 butterfly levels), maxima against the float64
-reference (scipy.signal.resample, omega4/panels/professional_meters.py:283-299).
+reference (scipy.signal.resample, omega4/panels/professional_meters.py:283-299).  `forward_half=False` emulates the
+r02k kernel (float32 forward transform, spectrum rounded to half).
 
     python tests/tools/truepeak16_numerics.py [SEED] [N_PAIRS]
 
@@ -45,13 +46,25 @@ def tp_ref(x):
     return 20 * np.log10(p) if p >= 1e-10 else -100.0
 
 
-def tp_emulated(xa, xb):
+_idx = np.arange(W)
+_REV = np.zeros(W, dtype=np.int64)
+for _b in range(11):
+    _REV |= ((_idx >> _b) & 1) << (10 - _b)
+
+
+def tp_emulated(xa, xb, forward_half=True):
     pk = max(np.abs(xa).max(), 1e-30), max(np.abs(xb).max(), 1e-30)
     z = (xa / pk[0]).astype(np.float32) + 1j * (xb / pk[1]).astype(np.float32)
-    Z = np.fft.fft(z.astype(np.complex64)).astype(np.complex64)
+    if forward_half:
+        fr, fi = fft_h(z.real.astype(h), z.imag.astype(h))      # decimation in frequency: bit-reversed order out
+        Zr = np.empty(W, dtype=h); Zi = np.empty(W, dtype=h)
+        Zr[_REV] = fr; Zi[_REV] = fi
+    else:
+        Z = np.fft.fft(z.astype(np.complex64)).astype(np.complex64)
+        Zr = Z.real.astype(h); Zi = Z.imag.astype(h)
     best = np.array([1.0, 1.0])
     for R in ROT:
-        Zr = Z.real.astype(h); Zi = Z.imag.astype(h); Rr = R.real.astype(h); Ri = R.imag.astype(h)
+        Rr = R.real.astype(h); Ri = R.imag.astype(h)
         sr = fma_h(Zr, Rr, -(Zi * Ri).astype(h)); si = fma_h(Zr, Ri, (Zi * Rr).astype(h))
         yr, yi = fft_h(sr, (-si.astype(np.float32)).astype(h))
         best[0] = max(best[0], np.abs(yr.astype(np.float64)).max() / W); best[1] = max(best[1], np.abs(yi.astype(np.float64)).max() / W)
@@ -77,12 +90,12 @@ def rand_frame(rng):
     return kind, x
 
 
-def run(seed, n_pairs):
+def run(seed, n_pairs, forward_half=True):
     rng = np.random.default_rng(seed)
     errs, kinds = [], []
     for _ in range(n_pairs):
         ka, xa = rand_frame(rng); kb, xb = rand_frame(rng)
-        ea, eb = tp_emulated(xa, xb)
+        ea, eb = tp_emulated(xa, xb, forward_half)
         errs += [abs(ea - tp_ref(xa)), abs(eb - tp_ref(xb))]; kinds += [ka, kb]
     return np.array(errs), np.array(kinds)
 
@@ -90,8 +103,9 @@ def run(seed, n_pairs):
 if __name__ == "__main__":
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 250
-    e, k = run(seed, n)
-    print("half-precision delayed phases, %d frames, seed %d: |dBTP error| max %.5f  p99 %.5f  median %.5f  (bar 0.05)" %
-          (len(e), seed, e.max(), np.percentile(e, 99), np.median(e)))
-    for i, name in enumerate(KINDS):
-        if (k == i).any(): print("  %-14s max %.5f  median %.5f  (%d frames)" % (name, e[k == i].max(), np.median(e[k == i]), (k == i).sum()))
+    for fh, what in ((True, "all four transforms in half (truepeak16_kernel)"), (False, "float32 forward transform, delayed phases in half (r02k)")):
+        e, k = run(seed, n, fh)
+        print("%s, %d frames, seed %d: |dBTP error| max %.5f  p99 %.5f  median %.5f  (bar 0.05)" %
+              (what, len(e), seed, e.max(), np.percentile(e, 99), np.median(e)))
+        for i, name in enumerate(KINDS):
+            if (k == i).any(): print("  %-14s max %.5f  median %.5f  (%d frames)" % (name, e[k == i].max(), np.median(e[k == i]), (k == i).sum()))

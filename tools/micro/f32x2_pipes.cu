@@ -3,6 +3,7 @@
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o f32x2_pipes f32x2_pipes.cu
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 template <int MODE, int LDS_PER_8>
 __global__ void k(float* out, int iters) {
@@ -28,6 +29,43 @@ __global__ void k(float* out, int iters) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc += v[c].x + v[c].y;
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// half2: one HADD2 / HFMA2 per element and iteration (two half lanes each)
+template <int MODE>
+__global__ void kh(float* out, int iters) {
+    __half2 v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = __floats2half2_rn(threadIdx.x * 1e-3f + c, threadIdx.x * 1e-3f - c);
+    const __half2 a = __floats2half2_rn(1e-3f, 2e-3f), m = __floats2half2_rn(1.0009f, 0.9991f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (MODE == 0) v[c] = __hadd2(v[c], a);
+            if (MODE == 1) v[c] = __hfma2(v[c], m, a);
+            if (MODE == 2) v[c] = __hmul2(v[c], m);
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc += __low2float(v[c]) + __high2float(v[c]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <int MODE>
+void runh(const char* name, int warps, int sms) {
+    float* out; cudaMalloc(&out, 4 << 22);
+    const int iters = 4000;
+    kh<MODE><<<sms, 32 * warps>>>(out, 10);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    kh<MODE><<<sms, 32 * warps>>>(out, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    int khz; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double cyc = ms * 1e-3 * khz * 1e3;
+    const double inst_lane = (double)iters * 32 * warps * 32;     // 32 half2 instructions per thread and iteration
+    printf("%-22s warps/SM %2d: %.1f half2 instruction lanes/clk/SM (= %.2f warp instructions/clk/SM)\n", name, warps, inst_lane / cyc, inst_lane / cyc / 32);
+    cudaFree(out);
 }
 
 template <int MODE, int L>
@@ -56,5 +94,6 @@ int main() {
     run<2, 4>("FFMA scalar + LDS", 16, sms);  run<3, 4>("FFMA2 packed + LDS", 16, sms);
     run<0, 8>("FADD scalar + LDS", 16, sms);  run<1, 8>("FADD2 packed + LDS", 16, sms);
     run<0, 0>("FADD scalar", 8, sms);   run<1, 0>("FADD2 packed", 8, sms);
+    runh<0>("HADD2", 16, sms); runh<1>("HFMA2", 16, sms); runh<2>("HMUL2", 16, sms); runh<1>("HFMA2", 8, sms);
     return 0;
 }
