@@ -606,9 +606,13 @@ def main():
             fp32 = None
             if kflop:
                 tf = k_hops * kflop / (ktimes[dom] / 1e3) / 1e12
+                note = "FFT butterflies are additions, not FMAs: at 100 % issue this instruction mix reaches about half the FMA peak"
+                if dom == "true_peak" and not (args.flags & N.FLAG_EXACT_TRUE_PEAK):
+                    note += ("; the kernel's transforms run as half2 instructions, which occupy the FMA pipe at the float32 rate "
+                             "per scalar operation (HFMA2 1.9 against FFMA 3.7 warp instructions per clock and SM, "
+                             "profiles/r02l_f32x2_pipes.txt), so the nominal float32 count still measures the pipe")
                 fp32 = {"flop_per_channel_hop": kflop, "achieved_tflops": tf, "peak_tflops_measured": FP32_PEAK_TFLOPS,
-                        "frac": tf / FP32_PEAK_TFLOPS,
-                        "note": "FFT butterflies are additions, not FMAs: at 100 % issue this instruction mix reaches about half the FMA peak"}
+                        "frac": tf / FP32_PEAK_TFLOPS, "note": note}
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "peak_source": peak_kind, "kernel_ms": ktimes[dom], "fp32": fp32,
                     "kernel_share_of_step": ktimes[dom] / sum(ktimes.values()),

@@ -38,17 +38,33 @@ __global__ void kh(float* out, int iters) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = __floats2half2_rn(threadIdx.x * 1e-3f + c, threadIdx.x * 1e-3f - c);
     const __half2 a = __floats2half2_rn(1e-3f, 2e-3f), m = __floats2half2_rn(1.0009f, 0.9991f);
+    float f[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) f[c] = threadIdx.x * 1e-3f + c;
     for (int i = 0; i < iters; ++i) {
+        if (MODE == 6) {            // 16 HFMA2 + 16 FFMA interleaved: do float32 and half2 share the pipe?
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { v[c] = __hfma2(v[c], m, a); f[c] = fmaf(f[c], 1.0000001f, 1e-9f); }
+        }
+        if (MODE == 7) {            // 16 HADD2 + 16 FFMA interleaved
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { v[c] = __hadd2(v[c], a); f[c] = fmaf(f[c], 1.0000001f, 1e-9f); }
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             if (MODE == 0) v[c] = __hadd2(v[c], a);
             if (MODE == 1) v[c] = __hfma2(v[c], m, a);
             if (MODE == 2) v[c] = __hmul2(v[c], m);
+            if (MODE == 3) v[c] = (c & 1) ? __hadd2(v[c], a) : __hfma2(v[c], m, a);          // HADD2 / HFMA2 alternating
+            if (MODE == 4) v[c] = (c & 1) ? __hmul2(v[c], m) : __hfma2(v[c], m, a);          // HMUL2 / HFMA2 alternating
+            if (MODE == 5) v[c] = (c & 1) ? __hadd2(v[c], a) : __hmul2(v[c], m);             // HADD2 / HMUL2 alternating
         }
     }
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc += __low2float(v[c]) + __high2float(v[c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc += f[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 template <int MODE>
@@ -95,5 +111,7 @@ int main() {
     run<0, 8>("FADD scalar + LDS", 16, sms);  run<1, 8>("FADD2 packed + LDS", 16, sms);
     run<0, 0>("FADD scalar", 8, sms);   run<1, 0>("FADD2 packed", 8, sms);
     runh<0>("HADD2", 16, sms); runh<1>("HFMA2", 16, sms); runh<2>("HMUL2", 16, sms); runh<1>("HFMA2", 8, sms);
+    runh<3>("HADD2 / HFMA2 mix", 16, sms); runh<4>("HMUL2 / HFMA2 mix", 16, sms); runh<5>("HADD2 / HMUL2 mix", 16, sms);
+    runh<6>("16 HFMA2 + 16 FFMA", 16, sms); runh<7>("16 HADD2 + 16 FFMA", 16, sms);
     return 0;
 }
