@@ -22,11 +22,26 @@
 
 namespace o4 {
 
+// Complex arithmetic on (re, im) register pairs.  Additions, the sqrt(1/2) rotations and element-wise products are
+// issued as packed float32 instructions (add.f32x2 / mul.f32x2, sm_100: FADD2 / FMUL2): the same IEEE operations bit
+// for bit, one issue slot instead of two (the FMA pipe's lane rate is unchanged, tools/micro/f32x2_pipes.cu), which is
+// what these kernels are short of next to their shared-memory traffic: N = 2048 -8 %, N = 1024 -5 % (r02m).  ptxas
+// folds the (a.y, -a.x) swaps and half negations into operand selectors (.LO_HI, .NP), no moves.  The general complex
+// product stays scalar: its packed form (FMUL2 + FFMA2 with broadcast selectors) is also bit-identical, but pairs up
+// registers until ptxas pays for it in moves -- measured slower (N = 1024: 3.83 -> 4.10 ms at 256 streams x 30 s).
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// a * (r, -r) and a * (-r, -r), r = sqrt(1/2): one FADD2 + one FMUL2 each
+__device__ __forceinline__ float2 rot_m45(float2 a, float r) {
+    return __fmul2_rn(__fadd2_rn(a, make_float2(a.y, -a.x)), make_float2(r, r));
+}
+__device__ __forceinline__ float2 rot_m135(float2 a, float r) {
+    return __fmul2_rn(__fadd2_rn(make_float2(a.y, -a.x), make_float2(-a.x, -a.y)), make_float2(r, r));
+}
+__device__ __forceinline__ float2 cmul_elem(float2 a, float2 b) { return __fmul2_rn(a, b); }      // (a.x b.x, a.y b.y)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 // multiply by -i : (x, y) -> (y, -x)
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
@@ -51,9 +66,9 @@ __device__ __forceinline__ void bf8(float2* v) {
     bf4(e0, e1, e2, e3);
     bf4(o0, o1, o2, o3);
     // twiddle o_c by W8^c
-    o1 = make_float2((o1.x + o1.y) * r, (o1.y - o1.x) * r);      // * (r, -r)
+    o1 = rot_m45(o1, r);                                         // * (r, -r)
     o2 = mul_mi(o2);                                             // * -i
-    o3 = make_float2((o3.y - o3.x) * r, -(o3.x + o3.y) * r);     // * (-r, -r)
+    o3 = rot_m135(o3, r);                                        // * (-r, -r)
     v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
     v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
     v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
@@ -71,15 +86,15 @@ __device__ __forceinline__ void bf16pt(float2* v) {
     // twiddle t[a][c] *= W16^{a*c}   (v index a + 4c)
     // a=1: c=1 -> W^1, c=2 -> W^2, c=3 -> W^3
     v[1 + 4]  = cmul(v[1 + 4],  make_float2(c1, -s1));
-    v[1 + 8]  = make_float2((v[1 + 8].x + v[1 + 8].y) * r, (v[1 + 8].y - v[1 + 8].x) * r);
+    v[1 + 8]  = rot_m45(v[1 + 8], r);
     v[1 + 12] = cmul(v[1 + 12], make_float2(s1, -c1));
     // a=2: c=1 -> W^2, c=2 -> W^4 = -i, c=3 -> W^6 = (-r,-r)
-    v[2 + 4]  = make_float2((v[2 + 4].x + v[2 + 4].y) * r, (v[2 + 4].y - v[2 + 4].x) * r);
+    v[2 + 4]  = rot_m45(v[2 + 4], r);
     v[2 + 8]  = mul_mi(v[2 + 8]);
-    v[2 + 12] = make_float2((v[2 + 12].y - v[2 + 12].x) * r, -(v[2 + 12].x + v[2 + 12].y) * r);
+    v[2 + 12] = rot_m135(v[2 + 12], r);
     // a=3: c=1 -> W^3, c=2 -> W^6, c=3 -> W^9 = -W^1
     v[3 + 4]  = cmul(v[3 + 4],  make_float2(s1, -c1));
-    v[3 + 8]  = make_float2((v[3 + 8].y - v[3 + 8].x) * r, -(v[3 + 8].x + v[3 + 8].y) * r);
+    v[3 + 8]  = rot_m135(v[3 + 8], r);
     v[3 + 12] = cmul(v[3 + 12], make_float2(-c1, s1));
     // step 2: for c: radix-4 over a -> out[c + 4d] ; t[a][c] sits at v[a + 4c]
 #pragma unroll
@@ -375,8 +390,10 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
 //   Zk = Z[k], Zm = Z[(M-k) % M], w = W_N^k = exp(-2 pi i k / N), N = 2M
 //   X[k] = E + w*O,  X[M-k] = conj(E - w*O),  E = (Zk + conj Zm)/2,  O = -i (Zk - conj Zm)/2
 __device__ __forceinline__ void rfft_pair(float2 Zk, float2 Zm, float2 w, float2& Xk, float2& Xmk) {
-    float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y - Zm.y));
-    float2 O = make_float2(0.5f * (Zk.y + Zm.y), -0.5f * (Zk.x - Zm.x));
+    // E = ((Zk.x + Zm.x) / 2, (Zk.y - Zm.y) / 2), O = ((Zk.y + Zm.y) / 2, -(Zk.x - Zm.x) / 2) as packed operations
+    const float2 hf = make_float2(0.5f, 0.5f);
+    float2 E = __fmul2_rn(__fadd2_rn(make_float2(Zm.x, -Zm.y), Zk), hf);
+    float2 O = __fmul2_rn(__fadd2_rn(make_float2(Zk.y, -Zk.x), make_float2(Zm.y, Zm.x)), hf);
     float2 T = cmul(w, O);
     Xk = cadd(E, T);
     float2 D = csub(E, T);

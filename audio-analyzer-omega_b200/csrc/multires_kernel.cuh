@@ -226,7 +226,7 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
         const bool active = valid && f >= a.first_frame;
         if (active && a.window) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { const float2 w = __ldg(wptr + j * TPF); v[j].x *= w.x; v[j].y *= w.y; }
+            for (int j = 0; j < 16; ++j) v[j] = cmul_elem(v[j], __ldg(wptr + j * TPF));
         }
         // the combine of the previous round runs right after this round's first barrier, which
         // also publishes the previous epilogue's magnitudes
@@ -322,7 +322,7 @@ multires_kernel(const __grid_constant__ MultiresArgs a) {
         const bool active = valid && f >= a.first_frame;
         if (active) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j].x *= win[j].x; v[j].y *= win[j].y; }
+            for (int j = 0; j < 16; ++j) v[j] = cmul_elem(v[j], win[j]);
         }
         const float2* Z = fft_forward<LOG2M, false>(v, buf0, buf1, st, t, active);
         {
