@@ -44,6 +44,7 @@ struct Kw32Sec {
     float phi[5][4];                // (M^65)^(2^j), row major
     float c16[4], c17[4];           // M^16, M^17
     float g[KW_SUBMAX][2];          // first row of M^(i+1)
+    float2 ga0[16], ga1[16];        // (g[k+1][e], g[k][e]), e = 0, 1: the forward correction of the (sub-chunk 0, sub-chunk 3) pair
 };
 
 struct Kweight32Args {
@@ -60,62 +61,111 @@ __device__ __forceinline__ float2 kw32_mat(const float* m, float2 s) {
     return make_float2(fmaf(m[0], s.x, m[1] * s.y), fmaf(m[2], s.x, m[3] * s.y));
 }
 
+// The lane's 65 samples as packed-float32 operands (add.f32x2 / fma.rn.f32x2, sm_100): the four independent sub-chunk
+// chains of a sweep run as TWO packed chains, so a step costs 5 issue slots per pair instead of 10 (the FMA pipe's lane
+// rate is the same, tools/micro/f32x2_pipes.cu; the kernel was short of issue slots: issue 67 %, FMA pipe 50 %).
+//   sub-chunk 0 = local samples 0 .. 16 (17), 1 = 17 .. 32, 2 = 33 .. 48, 3 = 49 .. 64 (16 each)
+//   a[k] = (sample 1 + k, sample 49 + k)      sub-chunk 0 without its first sample, paired with sub-chunk 3
+//   b[k] = (sample 17 + k, sample 33 + k)     sub-chunks 1 and 2
+//   r0   = sample 0: one scalar step before (forward) or after (backward) the 16 packed steps of its chain
+// Every element sees exactly the operations of the scalar formulation, in the same order: results are bit-identical
+// (tests/tools/kweight32_numerics.py emulates that order).
+struct Kw32R { float r0; float2 a[16]; float2 b[16]; };
+
+__device__ __forceinline__ float& kwr(Kw32R& q, int i) {               // local sample i, i a compile-time constant after unrolling
+    if (i == 0) return q.r0;
+    if (i <= 16) return q.a[i - 1].x;
+    if (i <= 32) return q.b[i - 17].x;
+    if (i <= 48) return q.b[i - 33].y;
+    return q.a[i - 49].y;
+}
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+
 template <bool BACKWARD>
-__device__ __forceinline__ void kw32_pass(float (&r)[KW_L], const Kw32Sec& c, int lane) {
+__device__ __forceinline__ void kw32_pass(Kw32R& q, const Kw32Sec& c, int lane) {
     const int pos = BACKWARD ? 31 - lane : lane;
     const float b0 = c.b0, a2 = c.a2, ngamma = -c.gamma, bb = c.bb;
-    // the two inputs preceding each sub-chunk, as (x[-1], x[-1] - x[-2]); sub-chunk m in processing order
-    float xa[KW_NSUB], dxa[KW_NSUB];
+    // the two inputs preceding each sub-chunk, as (x[-1], x[-1] - x[-2]), captured before anything is overwritten
+    float xa_in, dxa_in;                                                // the chain that starts at the lane boundary
     {
-        const float p1 = BACKWARD ? __shfl_down_sync(0xffffffffu, r[0], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 1], 1);
-        const float p2 = BACKWARD ? __shfl_down_sync(0xffffffffu, r[1], 1) : __shfl_up_sync(0xffffffffu, r[KW_L - 2], 1);
-        const float x0 = BACKWARD ? r[KW_L - 1] : r[0];                 // steady state: past inputs = first sample
-        xa[0] = pos == 0 ? x0 : p1;
-        dxa[0] = pos == 0 ? 0.f : p1 - p2;
+        const float p1 = BACKWARD ? __shfl_down_sync(0xffffffffu, kwr(q, 0), 1) : __shfl_up_sync(0xffffffffu, kwr(q, KW_L - 1), 1);
+        const float p2 = BACKWARD ? __shfl_down_sync(0xffffffffu, kwr(q, 1), 1) : __shfl_up_sync(0xffffffffu, kwr(q, KW_L - 2), 1);
+        const float x0 = BACKWARD ? kwr(q, KW_L - 1) : kwr(q, 0);       // steady state: past inputs = first sample
+        xa_in = pos == 0 ? x0 : p1;
+        dxa_in = pos == 0 ? 0.f : p1 - p2;
     }
-#pragma unroll
-    for (int m = 1; m < KW_NSUB; ++m) {
-        const int j = BACKWARD ? KW_NSUB - 1 - m : m;
-        xa[m] = BACKWARD ? r[kw_off(j + 1)] : r[kw_off(j) - 1];
-        dxa[m] = xa[m] - (BACKWARD ? r[kw_off(j + 1) + 1] : r[kw_off(j) - 2]);
+    const float2 s0 = make_float2(-b0 * xa_in, 0.f);                    // true entry state of the sequence (pos 0 only)
+    // pair A = (sub-chunk 0, sub-chunk 3), pair B = (sub-chunk 1, sub-chunk 2)
+    float2 xaA, dxaA, xaB, dxaB;
+    if (!BACKWARD) {
+        xaA = make_float2(xa_in, kwr(q, 48)); dxaA = make_float2(dxa_in, kwr(q, 48) - kwr(q, 47));
+        xaB = make_float2(kwr(q, 16), kwr(q, 32)); dxaB = make_float2(kwr(q, 16) - kwr(q, 15), kwr(q, 32) - kwr(q, 31));
+    } else {
+        xaA = make_float2(kwr(q, 17), xa_in); dxaA = make_float2(kwr(q, 17) - kwr(q, 18), dxa_in);
+        xaB = make_float2(kwr(q, 33), kwr(q, 49)); dxaB = make_float2(kwr(q, 33) - kwr(q, 34), kwr(q, 49) - kwr(q, 50));
     }
-    const float2 s0 = make_float2(-b0 * xa[0], 0.f);                     // true entry state of the sequence (pos 0 only)
-    // 1. zero-state sweeps, four independent chains
-    float z1[KW_NSUB], d1[KW_NSUB], y1[KW_NSUB];
+    // 1. zero-state sweeps
+    float2 zA = bc2(0.f), dA = bc2(0.f), yA = make_float2(b0 * xaA.x, b0 * xaA.y);
+    float2 zB = bc2(0.f), dB = bc2(0.f), yB = make_float2(b0 * xaB.x, b0 * xaB.y);
+    if (!BACKWARD) {                                                    // sub-chunk 0's first sample
+        const float x = q.r0;
+        const float t = fmaf(a2, dA.x, dxaA.x);
+        const float d = fmaf(ngamma, yA.x, t);
+        const float z = fmaf(bb, d, zA.x);
+        const float y = fmaf(b0, x, z);
+        dxaA.x = x - xaA.x; xaA.x = x; zA.x = z; dA.x = d; yA.x = y;
+        q.r0 = y;
+    }
+    const float2 A2 = bc2(a2), NG = bc2(ngamma), BB = bc2(bb), B0 = bc2(b0);
 #pragma unroll
-    for (int m = 0; m < KW_NSUB; ++m) { z1[m] = 0.f; d1[m] = 0.f; y1[m] = b0 * xa[m]; }
-#pragma unroll
-    for (int n = 0; n < KW_SUBMAX; ++n) {
-#pragma unroll
-        for (int m = 0; m < KW_NSUB; ++m) {
-            const int j = BACKWARD ? KW_NSUB - 1 - m : m;
-            const int len = kw_off(j + 1) - kw_off(j);
-            if (n < len) {
-                const int i = BACKWARD ? kw_off(j + 1) - 1 - n : kw_off(j) + n;
-                const float x = r[i];
-                const float t = fmaf(a2, d1[m], dxa[m]);
-                const float d = fmaf(ngamma, y1[m], t);
-                const float z = fmaf(bb, d, z1[m]);
-                const float y = fmaf(b0, x, z);
-                dxa[m] = x - xa[m]; xa[m] = x;
-                z1[m] = z; d1[m] = d; y1[m] = y;
-                r[i] = y;
-            }
+    for (int n = 0; n < 16; ++n) {
+        const int k = BACKWARD ? 15 - n : n;
+        {
+            const float2 x = q.a[k];
+            const float2 t = __ffma2_rn(A2, dA, dxaA);
+            const float2 d = __ffma2_rn(NG, yA, t);
+            const float2 z = __ffma2_rn(BB, d, zA);
+            const float2 y = __ffma2_rn(B0, x, z);
+            dxaA = __fadd2_rn(x, make_float2(-xaA.x, -xaA.y)); xaA = x; zA = z; dA = d; yA = y;
+            q.a[k] = y;
+        }
+        {
+            const float2 x = q.b[k];
+            const float2 t = __ffma2_rn(A2, dB, dxaB);
+            const float2 d = __ffma2_rn(NG, yB, t);
+            const float2 z = __ffma2_rn(BB, d, zB);
+            const float2 y = __ffma2_rn(B0, x, z);
+            dxaB = __fadd2_rn(x, make_float2(-xaB.x, -xaB.y)); xaB = x; zB = z; dB = d; yB = y;
+            q.b[k] = y;
         }
     }
+    if (BACKWARD) {                                                     // sub-chunk 0's last processed sample
+        const float x = q.r0;
+        const float t = fmaf(a2, dA.x, dxaA.x);
+        const float d = fmaf(ngamma, yA.x, t);
+        const float z = fmaf(bb, d, zA.x);
+        const float y = fmaf(b0, x, z);
+        zA.x = z; dA.x = d;
+        q.r0 = y;
+    }
+    // zero-state end states per sub-chunk, in processing order m = 0 .. 3
+    //   forward: sub-chunks 0, 1, 2, 3     backward: 3, 2, 1, 0
+    float2 e[KW_NSUB];
+    if (!BACKWARD) { e[0] = make_float2(zA.x, dA.x); e[1] = make_float2(zB.x, dB.x); e[2] = make_float2(zB.y, dB.y); e[3] = make_float2(zA.y, dA.y); }
+    else           { e[0] = make_float2(zA.y, dA.y); e[1] = make_float2(zB.y, dB.y); e[2] = make_float2(zB.x, dB.x); e[3] = make_float2(zA.x, dA.x); }
     // lane aggregate: zero-state end state of the whole 65-sample chunk
-    float2 v = make_float2(z1[0], d1[0]);
+    float2 v = e[0];
 #pragma unroll
     for (int m = 1; m < KW_NSUB; ++m) {
         const int j = BACKWARD ? KW_NSUB - 1 - m : m;
         const float* cm = (kw_off(j + 1) - kw_off(j) == 17) ? c.c17 : c.c16;
-        const float2 q = kw32_mat(cm, v);
-        v = make_float2(q.x + z1[m], q.y + d1[m]);
+        const float2 w = kw32_mat(cm, v);
+        v = make_float2(w.x + e[m].x, w.y + e[m].y);
     }
     // 2. scan of the chunk end states across lanes
     if (pos == 0) {
-        const float2 q = kw32_mat(c.phi[0], s0);
-        v.x += q.x; v.y += q.y;
+        const float2 w = kw32_mat(c.phi[0], s0);
+        v.x += w.x; v.y += w.y;
     }
 #pragma unroll
     for (int jj = 0; jj < 5; ++jj) {
@@ -123,8 +173,8 @@ __device__ __forceinline__ void kw32_pass(float (&r)[KW_L], const Kw32Sec& c, in
         const float rx = BACKWARD ? __shfl_down_sync(0xffffffffu, v.x, dd) : __shfl_up_sync(0xffffffffu, v.x, dd);
         const float ry = BACKWARD ? __shfl_down_sync(0xffffffffu, v.y, dd) : __shfl_up_sync(0xffffffffu, v.y, dd);
         if (pos >= dd) {
-            const float2 q = kw32_mat(c.phi[jj], make_float2(rx, ry));
-            v.x += q.x; v.y += q.y;
+            const float2 w = kw32_mat(c.phi[jj], make_float2(rx, ry));
+            v.x += w.x; v.y += w.y;
         }
     }
     float2 sin[KW_NSUB];
@@ -135,44 +185,67 @@ __device__ __forceinline__ void kw32_pass(float (&r)[KW_L], const Kw32Sec& c, in
     for (int m = 1; m < KW_NSUB; ++m) {
         const int jp = BACKWARD ? KW_NSUB - m : m - 1;
         const float* cm = (kw_off(jp + 1) - kw_off(jp) == 17) ? c.c17 : c.c16;
-        const float2 q = kw32_mat(cm, sin[m - 1]);
-        sin[m] = make_float2(q.x + z1[m - 1], q.y + d1[m - 1]);
+        const float2 w = kw32_mat(cm, sin[m - 1]);
+        sin[m] = make_float2(w.x + e[m - 1].x, w.y + e[m - 1].y);
     }
-    // 3. homogeneous correction (y = b0 x + z: the state only enters through z)
+    // 3. homogeneous correction (y = b0 x + z: the state only enters through z): sample of step n of a sub-chunk gets
+    //    g[n] . (entry state of that sub-chunk)
+    // entry states per pair component: A = (sub-chunk 0, sub-chunk 3), B = (sub-chunk 1, sub-chunk 2)
+    const float2 s_c0 = BACKWARD ? sin[3] : sin[0], s_c1 = BACKWARD ? sin[2] : sin[1];
+    const float2 s_c2 = BACKWARD ? sin[1] : sin[2], s_c3 = BACKWARD ? sin[0] : sin[3];
+    const float2 SXA = make_float2(s_c0.x, s_c3.x), SYA = make_float2(s_c0.y, s_c3.y);
+    const float2 SXB = make_float2(s_c1.x, s_c2.x), SYB = make_float2(s_c1.y, s_c2.y);
+    if (!BACKWARD) {
+        // sub-chunk 0: sample i is step i (r0: step 0, a[k].x: step k + 1); sub-chunks 1 .. 3: slot k is step k
+        q.r0 = fmaf(c.g[0][0], s_c0.x, fmaf(c.g[0][1], s_c0.y, q.r0));
 #pragma unroll
-    for (int n = 0; n < KW_SUBMAX; ++n) {
-#pragma unroll
-        for (int m = 0; m < KW_NSUB; ++m) {
-            const int j = BACKWARD ? KW_NSUB - 1 - m : m;
-            const int len = kw_off(j + 1) - kw_off(j);
-            if (n < len) {
-                const int i = BACKWARD ? kw_off(j + 1) - 1 - n : kw_off(j) + n;
-                r[i] = fmaf(c.g[n][0], sin[m].x, fmaf(c.g[n][1], sin[m].y, r[i]));
-            }
+        for (int k = 0; k < 16; ++k) {
+            q.a[k] = __ffma2_rn(c.ga0[k], SXA, __ffma2_rn(c.ga1[k], SYA, q.a[k]));
+            q.b[k] = __ffma2_rn(bc2(c.g[k][0]), SXB, __ffma2_rn(bc2(c.g[k][1]), SYB, q.b[k]));
         }
+    } else {
+        // descending: slot k of every sub-chunk is step 15 - k; sub-chunk 0's sample 0 is step 16
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float2 G0 = bc2(c.g[15 - k][0]), G1 = bc2(c.g[15 - k][1]);
+            q.a[k] = __ffma2_rn(G0, SXA, __ffma2_rn(G1, SYA, q.a[k]));
+            q.b[k] = __ffma2_rn(G0, SXB, __ffma2_rn(G1, SYB, q.b[k]));
+        }
+        q.r0 = fmaf(c.g[16][0], s_c0.x, fmaf(c.g[16][1], s_c0.y, q.r0));
     }
 }
 
 // odd reflection padding (9 samples) around the frame held at ext positions [9, 2057); the slack of lane 31
 // continues the last padded sample (constant input keeps the steady state, see the header)
-__device__ __forceinline__ void kw32_odd_pad(float (&r)[KW_L], int lane) {
+__device__ __forceinline__ void kw32_odd_pad(Kw32R& q, int lane) {
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[j] = 2.f * r[KW_PAD] - r[2 * KW_PAD - j];
+        for (int j = 0; j < KW_PAD; ++j) kwr(q, j) = 2.f * kwr(q, KW_PAD) - kwr(q, 2 * KW_PAD - j);
     }
     if (lane == 31) {
         constexpr int E = KW_LAST - KW_PAD;
 #pragma unroll
-        for (int j = 0; j < KW_PAD; ++j) r[E + 1 + j] = 2.f * r[E] - r[E - 1 - j];
+        for (int j = 0; j < KW_PAD; ++j) kwr(q, E + 1 + j) = 2.f * kwr(q, E) - kwr(q, E - 1 - j);
 #pragma unroll
-        for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = r[KW_LAST];
+        for (int i = KW_LAST + 1; i < KW_L; ++i) kwr(q, i) = kwr(q, KW_LAST);
     }
 }
 
-__device__ __forceinline__ void kw32_fill_slack(float (&r)[KW_L], int lane) {
+__device__ __forceinline__ void kw32_fill_slack(Kw32R& q, int lane) {
     if (lane == 31) {
 #pragma unroll
-        for (int i = KW_LAST + 1; i < KW_L; ++i) r[i] = r[KW_LAST];
+        for (int i = KW_LAST + 1; i < KW_L; ++i) kwr(q, i) = kwr(q, KW_LAST);
+    }
+}
+
+__device__ __forceinline__ void kw32_zero_pads(Kw32R& q, int lane) {
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < KW_PAD; ++i) kwr(q, i) = 0.f;
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int i = KW_LAST - KW_PAD + 1; i < KW_L; ++i) kwr(q, i) = 0.f;
     }
 }
 
@@ -219,13 +292,13 @@ kweight32_kernel(const __grid_constant__ Kweight32Args a) {
         __syncwarp();
         float* sl = stg + KW_STG_SHIFT + KW_L * lane;
         const float* hl = hann_x + KW_L * lane;
-        float r[KW_L];
+        Kw32R r;
         float sumsq = 0.f;
 #pragma unroll
         for (int i = 0; i < KW_L; ++i) {
             const float xv = sl[i] * hl[i];
             sumsq = fmaf(xv, xv, sumsq);
-            r[i] = xv;
+            kwr(r, i) = xv;
         }
         __syncwarp();
 #pragma unroll
@@ -248,17 +321,17 @@ kweight32_kernel(const __grid_constant__ Kweight32Args a) {
                 kw32_pass<true>(r, c, lane);
                 if (si == 0) {
                     // zero the pad positions and stash f (first filtfilt output) in the staging strip
-                    kw_zero_pads(r, lane);
+                    kw32_zero_pads(r, lane);
 #pragma unroll
-                    for (int i = 0; i < KW_L; ++i) sl[i] = r[i];
+                    for (int i = 0; i < KW_L; ++i) sl[i] = kwr(r, i);
                 }
             }
-            kw_zero_pads(r, lane);
+            kw32_zero_pads(r, lane);
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < KW_L; ++i) {
                 const float fv = sl[i];
-                const float w = fmaf(r[i] - fv, 0.3f, fv);               // f + (s - f) * 0.3 ; 0 at the pads
+                const float w = fmaf(kwr(r, i) - fv, 0.3f, fv);          // f + (s - f) * 0.3 ; 0 at the pads
                 acc = fmaf(w, w, acc);
             }
 #pragma unroll

@@ -513,6 +513,10 @@ static void build_kw32(const KwBiquad& q, Kw32Sec* o) {
         if (i + 1 == 17) for (int e = 0; e < 4; ++e) o->c17[e] = (float)P[e];
         if (i + 1 < KW_L) mat2_mul(M, P, P);
     }
+    for (int k = 0; k < 16; ++k) {
+        o->ga0[k] = make_float2(o->g[k + 1][0], o->g[k][0]);
+        o->ga1[k] = make_float2(o->g[k + 1][1], o->g[k][1]);
+    }
     double Q[4] = {P[0], P[1], P[2], P[3]};                     // M^65
     for (int j = 0; j < 5; ++j) {
         for (int e = 0; e < 4; ++e) o->phi[j][e] = (float)Q[e];
