@@ -213,13 +213,26 @@ __device__ __forceinline__ float tc_acc(uint32_t v, uint32_t c, float rs) {
 }
 // One hop-block row's operand scale for TC_F16: inv = 2^e with max |x| 2^-e in [0.5, 1) (1 for an all-zero row), so that
 // half's 5 exponent bits are spent on the 14 binades below the row's own maximum.  One warp per row.
-struct HopScaleArgs { const float* x; long long ch_stride; int hop, n_ch, j0, nb; float* inv; };
+// the scale of a row whose largest magnitude is m
+__device__ __forceinline__ float hop_row_scale(float m) {
+    int e = (int)((__float_as_uint(m) >> 23) & 0xffu);            // biased exponent: m = [1, 2) 2^(e - 127)
+    float inv = 1.f;
+    if (m > 0.f && e < 255) {                                     // (Inf / NaN rows keep scale 1: garbage in, garbage out)
+        e = e > 250 ? 250 : e;
+        inv = __uint_as_float((uint32_t)(e + 1) << 23);           // 2^(e - 126): denormal rows (e = 0) scale by 2^126
+    }
+    return inv;
+}
+// inv[ch][0 .. nb) belongs to hop blocks j0 .. j0 + nb - 1; this kernel fills the first `ncols` of them (all of them, or
+// only the blocks before the first meter frame when the K-weighting kernel of the same call writes the others: it has
+// every later hop block in registers anyway, kweight32_kernel.cuh)
+struct HopScaleArgs { const float* x; long long ch_stride; int hop, n_ch, j0, nb, ncols; float* inv; };
 __global__ void __launch_bounds__(256)
 hopblock_scale_kernel(const HopScaleArgs a) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= (long long)a.n_ch * a.nb) return;
-    const int ch = (int)(row / a.nb), j = (int)(row % a.nb);
+    if (row >= (long long)a.n_ch * a.ncols) return;
+    const int ch = (int)(row / a.ncols), j = (int)(row % a.ncols);
     const float4* px = reinterpret_cast<const float4*>(a.x + (long long)ch * a.ch_stride + ((long long)a.j0 + j) * a.hop);
     float m = 0.f;
     for (int i = lane; i < a.hop / 4; i += 32) {
@@ -228,15 +241,7 @@ hopblock_scale_kernel(const HopScaleArgs a) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) {
-        int e = (int)((__float_as_uint(m) >> 23) & 0xffu);        // biased exponent: m = [1, 2) 2^(e - 127)
-        float inv = 1.f;
-        if (m > 0.f && e < 255) {                                 // (Inf / NaN rows keep scale 1: garbage in, garbage out)
-            e = e > 250 ? 250 : e;
-            inv = __uint_as_float((uint32_t)(e + 1) << 23);       // 2^(e - 126): denormal rows (e = 0) scale by 2^126
-        }
-        a.inv[row] = inv;
-    }
+    if (lane == 0) a.inv[(size_t)ch * a.nb + j] = hop_row_scale(m);
 }
 
 

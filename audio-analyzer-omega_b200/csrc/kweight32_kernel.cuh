@@ -36,6 +36,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "kweight_kernel.cuh"
+#include "blockdft_tc_kernel.cuh"      // hop_row_scale
 
 namespace o4 {
 
@@ -54,6 +55,11 @@ struct Kweight32Args {
     const float* hann;              // [W] float32 Hann
     double* lufs_out;               // [n_ch][n_frames]
     int rms_gate, _align;
+    // optional by-product for the tensor-core hop-block GEMM of the same call (blockdft_tc_kernel.cuh): the operand scale
+    // of the hop block each frame ends with (hop 512: the last 128 float4 of the frame, already in registers here);
+    // hop_inv[ch][f - hop_inv_j0], row length hop_inv_nb.  nullptr: not wanted
+    float* hop_inv;
+    int hop_inv_nb, hop_inv_j0;
     Kw32Sec s[2];
 };
 
@@ -285,6 +291,15 @@ kweight32_kernel(const __grid_constant__ Kweight32Args a) {
         float4 tmp[KW_W / 4 / 32];
 #pragma unroll
         for (int j = 0; j < KW_W / 4 / 32; ++j) tmp[j] = __ldg(px + lane + 32 * j);
+        if (a.hop_inv) {                                                 // warp-uniform
+            float m = 0.f;
+#pragma unroll
+            for (int j = 3 * KW_W / 4 / 4 / 32; j < KW_W / 4 / 32; ++j)    // the frame's last quarter = hop block f
+                m = fmaxf(fmaxf(m, fmaxf(fabsf(tmp[j].x), fabsf(tmp[j].y))), fmaxf(fabsf(tmp[j].z), fabsf(tmp[j].w)));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) a.hop_inv[(size_t)ch * a.hop_inv_nb + (f - a.hop_inv_j0)] = hop_row_scale(m);
+        }
         if (lane < KW_PAD) stg[KW_STG_SHIFT + lane] = 0.f;
         if (lane < KW_SLACK + KW_PAD + KW_STG_SHIFT) stg[KW_STG_SHIFT + KW_PAD + KW_W + lane] = 0.f;
 #pragma unroll

@@ -449,7 +449,7 @@ struct omega4_plan {
     SparseSet set_cc;             // fp32 CUDA-core GEMM: up to 128 columns
     SparseSet set_tc;             // 3xTF32 tcgen05 GEMM: up to 512 columns
     bool tensor_default = true;   // OMEGA4_TENSOR=0 makes the CUDA-core GEMM the default
-    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32, scratch_comb, scratch_bstate;
+    DevBuf scratch_lufs, scratch_tp, scratch_mag[OMEGA4_MAX_RES], scratch_q, scratch_f32, scratch_comb, scratch_bstate, scratch_inv;
     DevBuf h_in, h_comb, h_meters, h_state, h_mag[OMEGA4_MAX_RES], h_f64a, h_f64b, h_f64c;
     // host-buffer mode: channel chunks are pipelined over N_SLOTS private streams / buffer sets so
     // that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
@@ -924,7 +924,7 @@ extern "C" void omega4_plan_destroy(omega4_plan* p) {
     }
     cudaFree(p->csr_ptr); cudaFree(p->csr_res); cudaFree(p->csr_lo); cudaFree(p->csr_frac);
     cudaFree(p->hann64); cudaFree(p->hann32); cudaFree(p->tp_rot); cudaFree(p->tp_rot_h);
-    p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release();
+    p->scratch_lufs.release(); p->scratch_tp.release(); p->scratch_q.release(); p->scratch_f32.release(); p->scratch_inv.release();
     p->scratch_comb.release(); p->scratch_bstate.release();
     p->set_cc.release(); p->set_tc.release();
     p->h_in.release(); p->h_comb.release(); p->h_meters.release(); p->h_state.release();
@@ -1040,6 +1040,34 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         CK(cudaEventRecord(sc->ev_fork, s));
         CK(cudaStreamWaitEvent(ms, sc->ev_fork, 0));
     }
+    // ---- which resolutions the hop-block GEMM serves, and its row range (needed before the meters: the K-weighting
+    // kernel can write the GEMM's per-row operand scales as a by-product)
+    const bool fused = p->disjoint;
+    int first[OMEGA4_MAX_RES];
+    bool use_sparse[OMEGA4_MAX_RES] = {false};
+    bool any_sparse = false;
+    const bool tensor = p->set_tc.n > 0 && (p->tensor_default ? !(flags & OMEGA4_FLAG_NO_TENSOR) : (flags & OMEGA4_FLAG_TENSOR) != 0);
+    const SparseSet& set = tensor ? p->set_tc : p->set_cc;
+    for (int r = 0; r < p->n_res; ++r) {
+        use_sparse[r] = combined && fused && set.of_res[r] >= 0 && !(mags && mags[r]) &&
+                        !(flags & OMEGA4_FLAG_NO_BLOCKDFT);
+        any_sparse = any_sparse || use_sparse[r];
+        // resolution r is filled once hist + (k+1) hop >= N
+        long long need = (long long)p->res[r].n - hist;
+        first[r] = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
+    }
+    int sp_j0 = 1 << 30;
+    for (int r = 0; r < p->n_res; ++r)
+        if (use_sparse[r]) { const int j = first[r] + 1 - set.sp[set.of_res[r]].B; if (j < sp_j0) sp_j0 = j; }
+    const int sp_nb = any_sparse ? n_hops - sp_j0 : 0;
+    float* row_inv = nullptr;                 // [n_ch][sp_nb] operand scales of the tensor-core GEMM's hop-block rows
+    int inv_from_kw = -1;                     // >= 0: the K-weighting kernel wrote the scales of hop blocks >= this index
+#if TC_F16
+    if (tensor && any_sparse && sp_nb > 0) {
+        int rc = p->scratch_inv.ensure((size_t)n_ch * sp_nb * sizeof(float)); if (rc) return rc;
+        row_inv = (float*)p->scratch_inv.p;
+    }
+#endif
     // ---- meters first: K-weighting on the meter stream, true peak on the caller's stream
     if (want_meters) {
         const size_t nser = (size_t)n_ch * n_hops * sizeof(double);
@@ -1055,6 +1083,10 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
             k.n_ch = n_ch; k.n_frames = n_hops; k.first_frame = first_m;
             k.frames_per_warp = n_hops >= 64 ? 8 : (n_hops >= 8 ? 2 : 1);
             k.hann = p->hann32; k.lufs_out = lufs; k.rms_gate = p->kw_gate;
+            if (row_inv && !concurrent && p->hop * 4 == p->W && first_m < n_hops && !getenv("OMEGA4_NO_SCALE_FOLD")) {
+                k.hop_inv = row_inv; k.hop_inv_nb = sp_nb; k.hop_inv_j0 = sp_j0;       // frame f ends with hop block f
+                inv_from_kw = first_m;
+            }
             build_kw32(p->kw[0], &k.s[0]); build_kw32(p->kw[1], &k.s[1]);
             Bracket b(p, ms, timing, "kweight_lufs");
             int rc = launch_kweight32(k, ms);
@@ -1110,23 +1142,9 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
         if (concurrent || stats_aside) CK(cudaEventRecord(sc->ev_join, ss));
     }
     // ---- multi-resolution FFTs (+ fused combine) on the caller's stream
-    const bool fused = p->disjoint;
     float* mag_ptr[OMEGA4_MAX_RES];
-    int first[OMEGA4_MAX_RES];
-    bool use_sparse[OMEGA4_MAX_RES] = {false};
-    bool any_sparse = false;
-    const bool tensor = p->set_tc.n > 0 && (p->tensor_default ? !(flags & OMEGA4_FLAG_NO_TENSOR) : (flags & OMEGA4_FLAG_TENSOR) != 0);
-    const SparseSet& set = tensor ? p->set_tc : p->set_cc;
-    for (int r = 0; r < p->n_res; ++r) {
-        use_sparse[r] = combined && fused && set.of_res[r] >= 0 && !(mags && mags[r]) &&
-                        !(flags & OMEGA4_FLAG_NO_BLOCKDFT);
-        any_sparse = any_sparse || use_sparse[r];
-    }
     for (int r = 0; r < p->n_res; ++r) {
         ResInfo& ri = p->res[r];
-        // resolution r is filled once hist + (k+1) hop >= N
-        long long need = (long long)ri.n - hist;
-        first[r] = need <= 0 ? 0 : (int)((need + p->hop - 1) / p->hop - 1);
         mag_ptr[r] = mags ? mags[r] : nullptr;
         if (combined && !fused && !mag_ptr[r]) {
             int rc = p->scratch_mag[r].ensure((size_t)n_ch * n_hops * ri.bins * sizeof(float));
@@ -1154,19 +1172,14 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
     }
     if (any_sparse) {
         // one GEMM over the hop blocks serves every sparse resolution; then one assembly per resolution
-        int j0 = 1 << 30;
-        for (int r = 0; r < p->n_res; ++r)
-            if (use_sparse[r]) { const int j = first[r] + 1 - set.sp[set.of_res[r]].B; if (j < j0) j0 = j; }
-        const int nb = n_hops - j0;
+        const int j0 = sp_j0, nb = sp_nb;
         const float* Q = nullptr;
         const bool fusedx = tensor && set.fusable;        // frames assembled in the GEMM epilogue, no Q
         if (nb > 0) {
             const size_t qbytes = fusedx ? (size_t)n_ch * set.nkx * n_hops * sizeof(float2)
                                          : (size_t)n_ch * nb * set.qs * sizeof(float);
-            const size_t qoff_scale = (qbytes + 255) & ~(size_t)255;           // [n_ch][nb] row scales behind Q / X
-            int rc = qbuf->ensure(qoff_scale + (tensor ? (size_t)n_ch * nb * sizeof(float) : 0));
+            int rc = qbuf->ensure(qbytes);
             if (rc) return rc;
-            (void)qoff_scale;
             Q = (float*)qbuf->p;
             if (tensor) {
                 BlockDftTcArgs g;
@@ -1177,12 +1190,16 @@ static int analyze_device(omega4_plan* p, cudaStream_t s, const float* x, long l
                 {   // per hop-block row operand scale (half's exponent range is spent below each row's own maximum)
                     HopScaleArgs h;
                     h.x = x; h.ch_stride = ch_stride; h.hop = p->hop; h.n_ch = n_ch; h.j0 = j0; h.nb = nb;
-                    h.inv = (float*)((char*)qbuf->p + qoff_scale);
+                    // hop blocks from inv_from_kw on have their scale from the K-weighting kernel of this call
+                    h.ncols = inv_from_kw >= 0 ? inv_from_kw - j0 : nb;
+                    h.inv = row_inv;
                     g.row_inv = h.inv; g.e_inv = set.e_inv;
-                    const long long rows = (long long)n_ch * nb;
-                    Bracket b(p, s, timing, "blockdft_row_scale");
-                    hopblock_scale_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h);
-                    CK(cudaGetLastError());
+                    const long long rows = (long long)n_ch * h.ncols;
+                    if (rows > 0) {
+                        Bracket b(p, s, timing, "blockdft_row_scale");
+                        hopblock_scale_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h);
+                        CK(cudaGetLastError());
+                    }
                 }
 #endif
                 if (fusedx) {
