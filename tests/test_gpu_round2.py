@@ -520,3 +520,30 @@ def test_single_frame_statistics_equal_the_walking_kernel(plan48, golden):
         # the true-peak kernel packs two frames per transform: a frame measured alone and the same frame packed with
         # its neighbour differ in the last float32 digit; the loudness columns do not depend on the pairing
         assert np.array_equal(out[:4], want[k, :4]) and abs(out[4] - want[k, 4]) <= 1e-5, k
+
+
+# ------------------------------------------------------------------ hop-block operand scales written by the K-weighting kernel
+def test_row_scales_from_the_kweighting_kernel_equal_the_separate_pass(plan48):
+    """The tensor-core GEMM's per-row operand scales come from the K-weighting kernel of the same call (it has every
+    hop block in registers) and from the stand-alone kernel only for the blocks before the first meter frame or the
+    carried history; OMEGA4_NO_SCALE_FOLD=1 keeps the separate pass.  Same scales -> bit-identical spectra, with and
+    without history, with rows of very different levels, and without meters (nothing to fold into)."""
+    rng = np.random.default_rng(11)
+    n_ch, n_hops = 5, 70
+    from omega4_b200 import _native as N
+    for hist in (0, 8192 - HOP):
+        x = rng.standard_normal((n_ch, hist + n_hops * HOP)).astype(np.float32)
+        x *= np.array([1.0, 1e-6, 30.0, 0.0, 0.2], dtype=np.float32)[:, None]
+        x[4, hist + 20 * HOP: hist + 24 * HOP] = 0.0                       # all-zero hop blocks inside a live row
+        a = plan48.analyze_host(x, hist_samples=hist, flags=N.FLAG_TIME_KERNELS)
+        t_fold = dict(plan48.kernel_times())
+        assert "blockdft_tc_gemm" in t_fold
+        os.environ["OMEGA4_NO_SCALE_FOLD"] = "1"
+        try:
+            b = plan48.analyze_host(x, hist_samples=hist, flags=N.FLAG_TIME_KERNELS)
+            assert "blockdft_row_scale" in dict(plan48.kernel_times())
+        finally:
+            os.environ.pop("OMEGA4_NO_SCALE_FOLD", None)
+        assert np.array_equal(a["combined"], b["combined"]) and np.array_equal(a["meters"], b["meters"])
+        c = plan48.analyze_host(x, hist_samples=hist, want_meters=False)
+        assert np.array_equal(a["combined"], c["combined"])
