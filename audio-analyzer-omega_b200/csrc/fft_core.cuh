@@ -331,9 +331,11 @@ __device__ __forceinline__ void load_local_twiddles(LocalTw<LOG2M>& st, const fl
 // MID is invoked by every thread right after the first barrier (used to overlap deferred work).
 // With KEEP_LAST_IN_REGS the final outputs stay in v[] (butterfly i of the last stage in
 // v[i*G2 .. i*G2+G2)) and nothing is written to Z.
+// zmask (group-uniform): bit pq set = the outputs k in [256 pq, 256 pq + 256) are stored to Z; a caller that reads only
+// part of the spectrum (fused epilogue) skips the stores of the other blocks.
 template <int LOG2M, bool KEEP_LAST_IN_REGS, typename TW, typename Mid>
 __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* Z, const TW& st,
-                                                  int t, int g, bool active, Mid&& mid) {
+                                                  int t, int g, bool active, Mid&& mid, unsigned zmask = 0xffffffffu) {
     constexpr int M = 1 << LOG2M;
     constexpr int TPF = M / 16;
     constexpr int G2 = M / 256;
@@ -378,7 +380,8 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
                 if (G2 == 16) bf16pt(v);
                 if (!KEEP_LAST_IN_REGS) {
 #pragma unroll
-                    for (int pq = 0; pq < G2; ++pq) Z[zq + 16 * G2 * i + 256 * pq] = v[i * G2 + pq];
+                    for (int pq = 0; pq < G2; ++pq)
+                        if (zmask & (1u << pq)) Z[zq + 16 * G2 * i + 256 * pq] = v[i * G2 + pq];
                 }
             }
         }

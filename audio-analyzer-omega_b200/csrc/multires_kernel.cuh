@@ -208,6 +208,18 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
         expand_local_twiddles<LOG2M>(st4, st);
     }
     const float2* wptr = reinterpret_cast<const float2*>(a.window) + t;
+    // fused mode: the epilogue untangles only the bins k in [need_lo, need_lo + need_cnt) and needs Z[k] and Z[M - k] for
+    // them; the 256-point blocks of the spectrum nobody reads are not stored (N = 2048: 2 of 4 blocks)
+    unsigned zmask = 0xffffffffu;
+    if (a.mag_out == nullptr && a.cplx_out == nullptr && a.need_cnt > 0) {
+        zmask = 0u;
+        const int lo = a.need_lo, hi = a.need_lo + a.need_cnt - 1;          // inclusive
+        const int mlo = M - hi, mhi = M - lo;                               // mirrored partners (index M wraps to 0)
+        for (int pq = 0; pq < (M / 256 > 0 ? M / 256 : 1); ++pq) {
+            const int b0 = 256 * pq, b1 = b0 + 255;
+            if ((lo <= b1 && hi >= b0) || (mlo <= b1 && mhi >= b0) || (pq == 0 && mhi >= M)) zmask |= 1u << pq;
+        }
+    }
 
     const float* xch = a.x + (long long)ch * a.ch_stride + a.frame_off0;
     float2 v[16];
@@ -237,7 +249,7 @@ multires_local_kernel(const __grid_constant__ MultiresArgs a) {
                     multires_combine<TPF>(a, ((r - 1) & 1) ? mags1 : mags0, t, (size_t)ch * a.n_frames + fp,
                                           fp >= a.first_frame, ctb);
             }
-        });
+        }, zmask);
         // prefetch the next round's samples; they land while the epilogue runs
         {
             const int fn = f + CONC;
