@@ -333,6 +333,9 @@ __device__ __forceinline__ void load_local_twiddles(LocalTw<LOG2M>& st, const fl
 // v[i*G2 .. i*G2+G2)) and nothing is written to Z.
 // zmask (group-uniform): bit pq set = the outputs k in [256 pq, 256 pq + 256) are stored to Z; a caller that reads only
 // part of the spectrum (fused epilogue) skips the stores of the other blocks.
+#ifndef FFT_LAST_STAGE_SHFL
+#define FFT_LAST_STAGE_SHFL 1
+#endif
 template <int LOG2M, bool KEEP_LAST_IN_REGS, typename TW, typename Mid>
 __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* Z, const TW& st,
                                                   int t, int g, bool active, Mid&& mid, unsigned zmask = 0xffffffffu) {
@@ -359,6 +362,30 @@ __device__ __forceinline__ void fft_forward_local(float2* v, float2* X, float2* 
             if (!KEEP_LAST_IN_REGS) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) Z[zaddr<LOG2M>(q + 16 * k)] = v[k];
+            }
+        } else if (G2 == 2 && FFT_LAST_STAGE_SHFL) {
+            // N = 1024: the last stage is a radix-2 butterfly between the two lanes of a pair (p = t & 1).  Each lane
+            // keeps the half of its values whose index has its own parity and trades the other half with its
+            // neighbour through the register crossbar (16 SHFL) instead of shared memory (16 STS.64 + 16 LDS.64):
+            // out0 = a + b is symmetric in the two lanes' values, out1 = a - b changes sign with the lane's parity --
+            // the same sums as the shared-memory exchange, bit for bit.
+            apply_twiddles(v, st.s2);
+            const int zq = zaddr<LOG2M>(q + 16 * p);
+            const float sgn = p ? -1.f : 1.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 keep = p ? v[2 * i + 1] : v[2 * i];          // v_p[p + 2 i]
+                const float2 send = p ? v[2 * i] : v[2 * i + 1];          // v_p[(1 - p) + 2 i]: the neighbour's index
+                float2 recv;
+                recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                v[2 * i] = cadd(keep, recv);                               // a + b
+                v[2 * i + 1] = cmul_elem(csub(keep, recv), make_float2(sgn, sgn));      // a - b = +-(keep - recv)
+                if (!KEEP_LAST_IN_REGS) {
+#pragma unroll
+                    for (int pq = 0; pq < 2; ++pq)
+                        if (zmask & (1u << pq)) Z[zq + 32 * i + 256 * pq] = v[2 * i + pq];
+                }
             }
         } else {
             apply_twiddles(v, st.s2);
