@@ -16,7 +16,7 @@
 // transforms, r02l) per 11.52 M frames.
 // Accuracy: a delayed phase only matters where it exceeds the sample peak, and then as a maximum of values of the
 // frame's own size; half keeps 11 significant bits through 11 butterfly levels, which leaves the peak within
-// ~2e-3 dB typically and 0.023 dB at worst of the float64 reference (north star: 0.05 dBTP; numpy emulation of this
+// ~2e-3 dB typically and 0.025 dB at worst (3600 emulated frames) of the float64 reference (north star: 0.05 dBTP; numpy emulation of this
 // arithmetic over sines, noise, clipped noise, square waves, impulses, random walks: tests/tools/truepeak16_numerics.py
 // -- the forward transform's rounding adds little to what the three inverse transforms carry: max 0.023 instead of
 // 0.022, p99 0.013 / 0.011 over 600 frames; on the GPU: the golden / stress tests, <= 0.021).  The float32 kernel
